@@ -1,0 +1,153 @@
+/*
+ * socp_b200.h -- C ABI of the B200 batched shooting engine (libsocp_b200.so).
+ *
+ * Drop-in boundary for the hot path of bherisse/socp.  The reference has no FFI of its own; its
+ * seams are (i) the C++ `model` / `shooting` classes and (ii) the cminpack callback ABI
+ * (`int fcn(void*, int, const real*, real*, int)`, src/socp/shooting.hpp:282, called from
+ * `hybrd` at src/socp/shooting.cpp:803-826).  Each entry point below names the reference code it
+ * replaces for a whole batch of independent problems.  The C++ host mirror of `model`/`shooting`
+ * (include/socp/) and the Python host (socp_b200/) both sit on top of exactly these symbols.
+ *
+ * Conventions: plain pointers and sizes only; the caller owns every buffer; int status return
+ * (0 = ok, <0 = error, message via socp_last_error); no exceptions cross the boundary; all work is
+ * ordered on the context's CUDA stream; one context per GPU and per host thread.
+ * `mem` selects where the caller's buffers live: SOCP_HOST (the library stages H2D / D2H itself)
+ * or SOCP_DEVICE (device pointers on the context's device; the call is asynchronous on the
+ * context stream until socp_sync()).  There is no CPU fallback: without a CUDA device
+ * socp_create fails.
+ *
+ * Data layouts (all double unless noted, row-major, one problem after another):
+ *   mparams [B][np]          model parameter block, index maps below (np = socp_model_nparams)
+ *   time    [B][M+1]         shooting::data_struct::time   (fixed node times)
+ *   Xb      [B][M+1][dim]    data->X[i][0..dim): boundary / waypoint states
+ *   x       [B][P]           unknowns (tab_param): M blocks of (state, costate), then FREE times
+ *   fvec    [B][P]           residual, layout of shooting::ShootingFunction (shooting.cpp:918-993)
+ *   fjac    [B][P*P]         column-major d fvec_i / d x_j at [i + j*P] (cminpack convention)
+ */
+#ifndef SOCP_B200_H
+#define SOCP_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* model ids: src/models/{goddard,doubleIntegrator,covid19,vtolUAV,interceptor} */
+enum { SOCP_GODDARD = 0, SOCP_DOUBLE_INTEGRATOR = 1, SOCP_COVID19 = 2, SOCP_VTOL_UAV = 3,
+       SOCP_INTERCEPTOR = 4, SOCP_NUM_MODELS = 5 };
+/* model::FIXED / FREE / CONTINUOUS (src/socp/model.hpp:34-38) */
+enum { SOCP_FIXED = 0, SOCP_FREE = 1, SOCP_CONTINUOUS = 2 };
+enum { SOCP_HOST = 0, SOCP_DEVICE = 1 };
+enum { SOCP_OK = 0, SOCP_ERR_ARG = -1, SOCP_ERR_CUDA = -2, SOCP_ERR_NOMEM = -3, SOCP_ERR_UNSUPPORTED = -4 };
+
+#define SOCP_MAX_NODES 64
+#define SOCP_MAX_DIM 7
+
+/* parameter block indices
+ * goddard (goddard.hpp:29-36):        C b KD kr u_max mu1 mu2 singularControl
+ * doubleIntegrator (.hpp:27-31):      u_max a_max muT
+ * covid19 (covid19.hpp:29-38):        R0 Tinf Tinc N Imax muI umin umax
+ * vtolUAV (vtolUAV.hpp:27-37) + obstacle (obstacle.hpp:24-29):
+ *                                     u_max a_max alphaT alphaV invSigmaXwp Vd ca nWP_tot nWP
+ *                                     phiObs psiWP muObs sigmaWP
+ * interceptor (interceptor.hpp:30-48): c0 hr d0 eta propellant_mass empty_mass q ve alpha_max
+ *                                     u_max a_max r_2p t_2p mu_gft muT muV muC                   */
+
+typedef struct socp_ctx socp_ctx;
+
+/* Shape shared by every problem of a batch = what shooting::SetMode / Resize fix
+ * (shooting.cpp:123-199).  step_nbr <= 0 selects the model's own stepNbr. */
+typedef struct {
+    int model_id;
+    int num_multi;
+    int step_nbr;
+    int mode_t[SOCP_MAX_NODES];
+    int mode_X[SOCP_MAX_NODES][SOCP_MAX_DIM];
+} socp_shape;
+
+typedef struct {
+    double rk4_steps;        /* RK4 steps executed by integration kernels since the last reset */
+    double kernel_launches;  /* kernels of this library launched since the last reset */
+    double solver_rounds;    /* lock-step rounds of the batched Powell-hybrid state machine */
+    double device_bytes;     /* workspace currently held on the device */
+} socp_stats;
+
+/* ---- context ------------------------------------------------------------------------------ */
+int socp_create(int device, socp_ctx **ctx);
+void socp_destroy(socp_ctx *ctx);
+const char *socp_last_error(const socp_ctx *ctx);      /* ctx may be NULL: last create error */
+int socp_set_stream(socp_ctx *ctx, void *cuda_stream); /* run on a caller-owned cudaStream_t */
+int socp_sync(socp_ctx *ctx);
+int socp_get_stats(socp_ctx *ctx, socp_stats *out);
+int socp_reset_stats(socp_ctx *ctx);
+/* wall-clock-free timing of the library's own kernels: CUDA events on the context stream */
+int socp_timer_start(socp_ctx *ctx);
+int socp_timer_stop(socp_ctx *ctx, float *ms);
+
+/* static facts */
+int socp_model_dim(int model_id);        /* model::GetDim (model.hpp:66) */
+int socp_model_nparams(int model_id);
+int socp_model_default_steps(int model_id);
+int socp_model_default_params(int model_id, double *out);     /* constructor defaults */
+int socp_num_param(const socp_shape *shape);                   /* shooting.cpp:179,196 */
+
+/* obstacle table of the vtolUAV penalty map (src/maps/obstacle/obstacle.cpp:24-36), shared by
+ * the whole context; type 0 ellipsoid, 1 box; pos/rad are [n][3].  Host pointers. */
+int socp_set_obstacles(socp_ctx *ctx, int n, const double *type, const double *pos, const double *rad);
+
+/* ---- hot path ------------------------------------------------------------------------------ */
+
+/* model::ComputeTraj (model.hpp:77; interceptor.cpp:165) for B independent trajectories:
+ * fixed-step RK4 (odeTools.cpp:89-98, :128-146), S = step_nbr steps per segment.
+ * sw: optional [B][2] goddard switching times (goddard.cpp:27-29, :373), NULL = defaults. */
+int socp_traj_batch(socp_ctx *ctx, int model_id, int step_nbr, long B, const double *mparams,
+                    const double *sw, const double *t0, const double *tf, const double *X0,
+                    double *Xf, int mem);
+
+/* odeTools::Model / model::Control / model::Hamiltonian at B points (rhs [B][2dim], control
+ * [B][4], H [B]); any output may be NULL.  chart_stage: optional [B][2] ints (interceptor). */
+int socp_point_batch(socp_ctx *ctx, int model_id, long B, const double *mparams, const double *sw,
+                     const int *chart_stage, const double *t, const double *X, double *rhs,
+                     double *control, double *H, int mem);
+
+/* shooting::ShootingFunction (shooting.cpp:918-993) for B problems. */
+int socp_residual_batch(socp_ctx *ctx, const socp_shape *shape, long B, const double *mparams,
+                        const double *time, const double *Xb, const double *x, double *fvec, int mem);
+
+/* MINPACK fdjac1 (dense) as hybrd applies it to the shooting residual: column j is
+ * (F(x + h_j e_j) - F(x)) / h_j, h_j = sqrt(epsfcn)|x_j| (or sqrt(epsfcn) if x_j == 0). */
+int socp_fdjac_batch(socp_ctx *ctx, const socp_shape *shape, long B, const double *mparams,
+                     const double *time, const double *Xb, const double *x, double epsfcn,
+                     double *fjac, int mem);
+
+/* shooting::SolveShootingFunction (shooting.cpp:781-856, modelOrder 0): Powell hybrid with the
+ * reference's settings (maxfev given, ml = mu = P-1, epsfcn = 1e-15, mode = 1, factor = 1).
+ * x is updated in place for EVERY problem (as hybrd does); info/nfev/fnorm are [B].
+ * SOCP accepts a solve iff info == 1 (shooting.cpp:588). */
+int socp_solve_batch(socp_ctx *ctx, const socp_shape *shape, long B, const double *mparams,
+                     const double *time, const double *Xb, double *x, double xtol, int maxfev,
+                     int *info, int *nfev, double *fnorm, int mem);
+
+/* shooting::SolveShootingContinuation on a model parameter (shooting.cpp:695-778), every problem
+ * running its own homotopy b in (0,1] with step halving.  mparams is updated in place (entry
+ * param_idx ends at goal[b] on success).  goal is [B].  calls is [B][2] = {solver calls, total
+ * nfev}.  Host buffers only. */
+int socp_continuation_param_batch(socp_ctx *ctx, const socp_shape *shape, long B, double *mparams,
+                                  const double *time, const double *Xb, double *x, double xtol,
+                                  int maxfev, double step, int param_idx, const double *goal,
+                                  double step_min, int *info, int *calls);
+
+/* shooting::SolveShootingContinuation on the boundary data (shooting.cpp:598-692): homotopy from
+ * (time_prec, Xb_prec) to (time_des, Xb_des).  Host buffers only. */
+int socp_continuation_boundary_batch(socp_ctx *ctx, const socp_shape *shape, long B,
+                                     const double *mparams, const double *time_prec,
+                                     const double *Xb_prec, const double *time_des,
+                                     const double *Xb_des, double *x, double xtol, int maxfev,
+                                     double step, double step_min, int *info, int *calls);
+
+/* FP64 FMA peak of the device measured with a register-resident DFMA chain (GFLOP/s). */
+int socp_measure_fp64_peak(socp_ctx *ctx, double *gflops, double *sm_clock_mhz);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,173 @@
+// socp_b200/csrc/integrate.cuh -- fixed-step RK4 on registers, one thread per trajectory.
+//
+// Restates odeTools::RK4 (/root/reference/src/socp/odeTools.cpp:89-98), odeTools::integrate
+// (:128-146, non-Boost branch), model::ModelInt (src/socp/model.hpp:395-414) and
+// interceptor::ComputeTraj / ModelInt (src/models/interceptor/interceptor.cpp:165-220, :104-130).
+// The state/costate vector, the stage slopes and the model constants stay in registers for the
+// whole segment; nothing is written until the end point.
+#pragma once
+#include "models.cuh"
+
+namespace socp {
+
+// One classical RK4 step with the reference's combination order
+//   X <- X + (h/6) * (F1 + (F4 + 2*(F2 + F3)))          (odeTools.cpp:97)
+template <int MODEL>
+SOCP_DEV void rk4_step(const typename Model<MODEL>::Ctx &c, double t, double *X, double h) {
+    typedef Model<MODEL> M;
+    constexpr int N = M::N;
+    double F1[N], F23[N], F[N], Y[N];
+    const double h2 = h / 2.0;
+    M::rhs(c, t, X, F1);
+#pragma unroll
+    for (int i = 0; i < N; ++i) Y[i] = X[i] + h2 * F1[i];
+    M::rhs(c, t + h2, Y, F23);                       // F2
+#pragma unroll
+    for (int i = 0; i < N; ++i) Y[i] = X[i] + h2 * F23[i];
+    M::rhs(c, t + h2, Y, F);                         // F3
+#pragma unroll
+    for (int i = 0; i < N; ++i) { F23[i] = F23[i] + F[i]; Y[i] = X[i] + h * F[i]; }
+    M::rhs(c, t + h, Y, F);                          // F4
+    const double h6 = h / 6.0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) X[i] = X[i] + h6 * (F1[i] + (F[i] + 2.0 * F23[i]));
+}
+
+// odeTools::integrate: `while (t < tf - dt/2)` with `t += dt` and a last-step clamp, so that
+// tf <= t0 performs zero steps.  Returns the number of RK4 steps taken.
+template <int MODEL>
+SOCP_DEV int integrate_fixed(const typename Model<MODEL>::Ctx &c, double *X, double t0, double tf, double dt) {
+    double t = t0;
+    int steps = 0;
+    while (t < (tf - dt / 2)) {
+        if (t + dt > tf) rk4_step<MODEL>(c, t, X, tf - t);
+        else rk4_step<MODEL>(c, t, X, dt);
+        t += dt;
+        ++steps;
+    }
+    return steps;
+}
+
+// model::ComputeTraj for one segment.  For the interceptor `c.chart` / `c.stage` are updated and
+// left as the reference leaves its hidden state (the final state is converted back to chart 1
+// but currentChart is not reset, interceptor.cpp:214-216).
+template <int MODEL>
+SOCP_DEV int compute_traj(typename Model<MODEL>::Ctx &c, double *X, double t0, double tf, int S) {
+    return integrate_fixed<MODEL>(c, X, t0, tf, (tf - t0) / S);
+}
+
+SOCP_DEV int interceptor_model_int(Model<INTERCEPTOR>::Ctx &c, double *X, double t0, double tf, int S) {
+    double t = t0;
+    const double dt = (tf - t0) / S;
+    for (int i = 0; i < S; ++i) {
+        Model<INTERCEPTOR>::set_chart(c, X);
+        rk4_step<INTERCEPTOR>(c, t, X, dt);
+        t += dt;
+    }
+    return S;
+}
+
+template <>
+SOCP_DEV int compute_traj<INTERCEPTOR>(Model<INTERCEPTOR>::Ctx &c, double *X, double t0, double tf, int S) {
+    int steps = 0;
+    c.chart = 1;
+    const double t1 = c.mprop / c.q;
+    if (t0 < t1) {
+        c.stage = 1;
+        if (tf > t1) {
+            steps += interceptor_model_int(c, X, t0, t1, S);
+            c.stage = 0;
+            steps += interceptor_model_int(c, X, t1, tf, S);
+        } else {
+            steps += interceptor_model_int(c, X, t0, tf, S);
+        }
+    } else {
+        c.stage = 0;
+        steps += interceptor_model_int(c, X, t0, tf, S);
+    }
+    if (c.chart == 2) Model<INTERCEPTOR>::convert(2, X);
+    return steps;
+}
+
+template <int MODEL> SOCP_DEV void get_chart_stage(const typename Model<MODEL>::Ctx &, int &chart, int &stage) { chart = 1; stage = 0; }
+template <> SOCP_DEV void get_chart_stage<INTERCEPTOR>(const Model<INTERCEPTOR>::Ctx &c, int &chart, int &stage) { chart = c.chart; stage = c.stage; }
+template <int MODEL> SOCP_DEV void set_chart_stage(typename Model<MODEL>::Ctx &, int, int) {}
+template <> SOCP_DEV void set_chart_stage<INTERCEPTOR>(Model<INTERCEPTOR>::Ctx &c, int chart, int stage) { c.chart = chart; c.stage = stage; }
+
+// warp-aggregated add of per-thread step counts into a device counter
+SOCP_DEV void count_steps(unsigned long long *counter, int steps) {
+    unsigned mask = __activemask();
+    int total = steps;
+    for (int off = 16; off > 0; off >>= 1) total += __shfl_down_sync(mask, total, off);
+    // lanes outside the mask contribute garbage only if the mask is not full; handle that case
+    if (mask != 0xffffffffu) {
+        atomicAdd(counter, (unsigned long long)steps);
+    } else if ((threadIdx.x & 31) == 0) {
+        atomicAdd(counter, (unsigned long long)total);
+    }
+}
+
+// ---- kernel: B independent trajectories ------------------------------------------------------
+template <int MODEL>
+__global__ void __launch_bounds__(128)
+traj_kernel(long B, int S, const double *__restrict__ mparams, const double *__restrict__ sw,
+            const double *__restrict__ t0, const double *__restrict__ tf,
+            const double *__restrict__ X0, double *__restrict__ Xf, unsigned long long *counter) {
+    typedef Model<MODEL> M;
+    constexpr int N = M::N;
+    long b = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    int steps = 0;
+    if (b < B) {
+        typename M::Ctx c;
+        M::load(c, mparams + b * M::NP, sw ? sw + 2 * b : nullptr);
+        double X[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) X[i] = X0[b * N + i];
+        steps = compute_traj<MODEL>(c, X, t0[b], tf[b], S);
+#pragma unroll
+        for (int i = 0; i < N; ++i) Xf[b * N + i] = X[i];
+    }
+    count_steps(counter, steps);
+}
+
+// ---- kernel: RHS / control / Hamiltonian at B points -----------------------------------------
+template <int MODEL>
+__global__ void point_kernel(long B, const double *__restrict__ mparams, const double *__restrict__ sw,
+                             const int *__restrict__ chart_stage, const double *__restrict__ t,
+                             const double *__restrict__ X, double *rhs, double *control, double *H) {
+    typedef Model<MODEL> M;
+    constexpr int N = M::N;
+    long b = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    typename M::Ctx c;
+    M::load(c, mparams + b * M::NP, sw ? sw + 2 * b : nullptr);
+    if (chart_stage) set_chart_stage<MODEL>(c, chart_stage[2 * b], chart_stage[2 * b + 1]);
+    double x[N], out[N];
+    for (int i = 0; i < N; ++i) x[i] = X[b * N + i];
+    if (rhs) {
+        M::rhs(c, t[b], x, out);
+        for (int i = 0; i < N; ++i) rhs[b * N + i] = out[i];
+    }
+    if (control) {
+        double u[4] = {0, 0, 0, 0};
+        M::control(c, t[b], x, u);
+        for (int i = 0; i < 4; ++i) control[b * 4 + i] = u[i];
+    }
+    if (H) H[b] = M::hamiltonian(c, t[b], x);
+}
+
+// ---- FP64 peak probe: register-resident DFMA chains ------------------------------------------
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double *out, int iters, double a, double b) {
+    double x0 = threadIdx.x * 1e-3, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5,
+           x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+            x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+        }
+    }
+    out[(long)blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+
+}  // namespace socp

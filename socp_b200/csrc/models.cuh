@@ -1,0 +1,619 @@
+// socp_b200/csrc/models.cuh -- device code of the five SOCP models (sm_100a, fp64).
+//
+// Each model is a struct with
+//     DIM, N = 2*DIM, NP (parameter block length), NCTRL
+//     struct Ctx     per-trajectory constants held in registers (parameters, switching times,
+//                    and -- interceptor -- the chart / stage the reference keeps as hidden
+//                    mutable model state, interceptor.cpp:27-29)
+//     load(ctx, mparams, sw)            fill Ctx from the parameter block
+//     rhs(ctx, t, X, dX)                odeTools::Model  = (dH/dp, -dH/dx) with the PMP control
+//     control(ctx, t, X, u)             model::Control
+//     hamiltonian(ctx, t, X)            model::Hamiltonian (isJac == 0)
+// The formulas restate /root/reference/src/models/*/*.cpp (file:line at each function); common
+// subexpressions (1/r, 1/m, exp(-kr(r-1)), sin/cos of the angles) are evaluated once, which
+// changes rounding by a few ulp only -- parity is checked to <= 1e-12 against the oracle.
+#pragma once
+#include <math.h>
+
+namespace socp {
+
+enum { GODDARD = 0, DOUBLE_INTEGRATOR = 1, COVID19 = 2, VTOL_UAV = 3, INTERCEPTOR = 4 };
+
+#define SOCP_MAX_OBS 32
+// obstacle table of the vtolUAV penalty map: per obstacle {type, pos[3], rad[3]} (obstacle.cpp:24-36)
+__constant__ double c_obstacles[SOCP_MAX_OBS * 7];
+__constant__ int c_num_obstacles;
+
+#define SOCP_DEV __device__ __forceinline__
+
+template <int MODEL> struct Model;
+
+// =============================== goddard ======================================================
+template <> struct Model<GODDARD> {
+    static constexpr int DIM = 7, N = 14, NP = 8, NCTRL = 3, DEFAULT_STEPS = 10;
+    struct Ctx { double C, b, KD, kr, umax, mu1, mu2, sing, sw0, sw1; };
+    SOCP_DEV static void load(Ctx &c, const double *m, const double *sw) {
+        c.C = m[0]; c.b = m[1]; c.KD = m[2]; c.kr = m[3]; c.umax = m[4]; c.mu1 = m[5]; c.mu2 = m[6];
+        c.sing = m[7];
+        c.sw0 = sw ? sw[0] : 0.0227;      // goddard.cpp:27-29
+        c.sw1 = sw ? sw[1] : 0.08;
+    }
+
+    // goddard.cpp:188-253 (true singular control), expression order of the reference
+    SOCP_DEV static double singular(const Ctx &c, const double *X) {
+        double x = X[0], y = X[1], z = X[2], vx = X[3], vy = X[4], vz = X[5], mass = X[6];
+        double p_x = X[7], p_y = X[8], p_z = X[9], p_vx = X[10], p_vy = X[11], p_vz = X[12];
+        double r = sqrt(x * x + y * y + z * z);
+        double v = sqrt(vx * vx + vy * vy + vz * vz);
+        double rdotv = x * vx + y * vy + z * vz;
+        double pvdotv = p_vx * vx + p_vy * vy + p_vz * vz;
+        double b = c.b, C = c.C, KD = c.KD, kr = c.kr;
+        double g = 1 / r / r;
+        double norm_pv = sqrt(p_vx * p_vx + p_vy * p_vy + p_vz * p_vz);
+        double ex = exp(-kr * (r - 1));
+        double D = KD * ex;
+        double p_xdot = -kr * KD / mass * v * ex * x / r * pvdotv + g * (p_vx * (1 - 3 * x * x / r / r) / r - p_vy * 3 * x * y / r / r / r - p_vz * 3 * x * z / r / r / r);
+        double p_ydot = -kr * KD / mass * v * ex * y / r * pvdotv + g * (-p_vx * 3 * y * x / r / r / r + p_vy * (1 - 3 * y * y / r / r) / r - p_vz * 3 * y * z / r / r / r);
+        double p_zdot = -kr * KD / mass * v * ex * z / r * pvdotv + g * (-p_vx * 3 * z * x / r / r / r - p_vy * 3 * z * y / r / r / r + p_vz * (1 - 3 * z * z / r / r) / r);
+        double p_vxdot = -p_x + KD / mass * ex * (pvdotv * vx / v + p_vx * v);
+        double p_vydot = -p_y + KD / mass * ex * (pvdotv * vy / v + p_vy * v);
+        double p_vzdot = -p_z + KD / mass * ex * (pvdotv * vz / v + p_vz * v);
+        double prdotdotpv = p_xdot * p_vx + p_ydot * p_vy + p_zdot * p_vz;
+        double prdotpvdot = p_x * p_vxdot + p_y * p_vydot + p_z * p_vzdot;
+        double prdotpv = p_x * p_vx + p_y * p_vy + p_z * p_vz;
+        double pvdotdotv = p_vxdot * vx + p_vydot * vy + p_vzdot * vz;
+        double pvdotdotpv = p_vxdot * p_vx + p_vydot * p_vy + p_vzdot * p_vz;
+        double vdotg = vx * g * x / r + vy * g * y / r + vz * g * z / r;
+        double pvdotg = p_vx * g * x / r + p_vy * g * y / r + p_vz * g * z / r;
+        double au = 2 * norm_pv * C / mass * pvdotv + 2 * pvdotv * C / mass * norm_pv
+                  - b / mass * (2 * pvdotv * pvdotv + norm_pv * norm_pv * v * v)
+                  - b / D * v * prdotpv - C / D * prdotpv / v * pvdotv / norm_pv;
+        double bu = -2 * norm_pv * norm_pv * (vdotg + D / mass * v * v * v) + 2 * v * v * pvdotdotpv
+                  - 2 * pvdotv * (pvdotg + D / mass * v * pvdotv - pvdotdotv)
+                  + b / C * (2 * norm_pv * pvdotv * (vdotg + D / mass * v * v * v) + norm_pv * v * v * (pvdotg + D / mass * v * pvdotv - pvdotdotv) - v * v * pvdotv / norm_pv * pvdotdotpv)
+                  - mass / D * kr * rdotv / r * v * prdotpv + mass / D * prdotpv / v * (vdotg + D / mass * v * v * v) - mass / D * v * (prdotdotpv + prdotpvdot);
+        return bu / au;
+    }
+
+    // goddard.cpp:104-185.  Returns the control and |u| (= min(|alpha_u|, u_max)).
+    SOCP_DEV static void control_norm(const Ctx &c, double t, const double *X, double minv,
+                                      double *u, double &norm_u) {
+        double p_vx = X[10], p_vy = X[11], p_vz = X[12], p_mass = X[13];
+        double norm_pv = sqrt(p_vx * p_vx + p_vy * p_vy + p_vz * p_vz);
+        double Switch = c.mu1 - c.b * p_mass - c.C * minv * norm_pv;
+        double alpha_u = 0.0;
+        if (c.mu2 > 0) {
+            if (Switch < 0) alpha_u = -Switch / 2 / c.mu2;
+        } else {
+            if (t <= c.sw0) alpha_u = 1.0;
+            else if (t <= c.sw1) alpha_u = (c.sing < 0) ? singular(c, X) : c.sing;
+        }
+        double a = fabs(alpha_u);
+        double scale = -alpha_u / norm_pv;          // u = -p_v * alpha_u / |p_v|
+        norm_u = a;
+        if (a > c.umax) { scale = scale / a * c.umax; norm_u = c.umax; }
+        u[0] = p_vx * scale; u[1] = p_vy * scale; u[2] = p_vz * scale;
+    }
+    SOCP_DEV static void control(const Ctx &c, double t, const double *X, double *u) {
+        double nu;
+        control_norm(c, t, X, 1.0 / X[6], u, nu);
+    }
+
+    // goddard.cpp:48-101
+    SOCP_DEV static void rhs(const Ctx &c, double t, const double *X, double *dX) {
+        double x = X[0], y = X[1], z = X[2], vx = X[3], vy = X[4], vz = X[5], mass = X[6];
+        double p_x = X[7], p_y = X[8], p_z = X[9], p_vx = X[10], p_vy = X[11], p_vz = X[12];
+        double r2 = x * x + y * y + z * z;
+        double r = sqrt(r2);
+        double rinv = 1.0 / r;
+        double v = sqrt(vx * vx + vy * vy + vz * vz);
+        double vinv = 1.0 / v;
+        double minv = 1.0 / mass;
+        double pvdotv = p_vx * vx + p_vy * vy + p_vz * vz;
+        double ex = exp(-c.kr * (r - 1));
+        double g = rinv * rinv;                      // normalised gravity 1/r^2
+        double u[3], norm_u;
+        control_norm(c, t, X, minv, u, norm_u);
+        double pvdotu = p_vx * u[0] + p_vy * u[1] + p_vz * u[2];
+        double Dm = c.KD * ex * minv;                // KD exp(-kr(r-1)) / m
+        double drag = Dm * v;
+        double gr = g * rinv;                        // 1/r^3
+        double Cm = c.C * minv;
+        dX[0] = vx; dX[1] = vy; dX[2] = vz;
+        dX[3] = -drag * vx - gr * x + Cm * u[0];
+        dX[4] = -drag * vy - gr * y + Cm * u[1];
+        dX[5] = -drag * vz - gr * z + Cm * u[2];
+        dX[6] = -c.b * norm_u;
+        double kd = c.kr * drag * rinv * pvdotv;     // kr KD/m v e^.. pv.v / r
+        double xdotpv = x * p_vx + y * p_vy + z * p_vz;
+        double w = 3.0 * xdotpv * g;                 // 3 (x.p_v) / r^2
+        dX[7] = -kd * x + gr * (p_vx - w * x);
+        dX[8] = -kd * y + gr * (p_vy - w * y);
+        dX[9] = -kd * z + gr * (p_vz - w * z);
+        double pv_v = pvdotv * vinv;
+        dX[10] = -p_x + Dm * (pv_v * vx + p_vx * v);
+        dX[11] = -p_y + Dm * (pv_v * vy + p_vy * v);
+        dX[12] = -p_z + Dm * (pv_v * vz + p_vz * v);
+        dX[13] = -Dm * minv * v * pvdotv + Cm * minv * pvdotu;
+    }
+
+    // goddard.cpp:256-295
+    SOCP_DEV static double hamiltonian(const Ctx &c, double t, const double *X) {
+        double x = X[0], y = X[1], z = X[2], vx = X[3], vy = X[4], vz = X[5], mass = X[6];
+        double p_x = X[7], p_y = X[8], p_z = X[9], p_vx = X[10], p_vy = X[11], p_vz = X[12], p_mass = X[13];
+        double r = sqrt(x * x + y * y + z * z);
+        double v = sqrt(vx * vx + vy * vy + vz * vz);
+        double ex = exp(-c.kr * (r - 1));
+        double g = 1 / r / r;
+        double u[3], nu;
+        control_norm(c, t, X, 1.0 / mass, u, nu);
+        double norm_u = sqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
+        return c.mu1 * norm_u + c.mu2 * norm_u * norm_u + p_x * vx + p_y * vy + p_z * vz
+             + p_vx * (-c.KD * v * vx * ex / mass - g * x / r + c.C * u[0] / mass)
+             + p_vy * (-c.KD * v * vy * ex / mass - g * y / r + c.C * u[1] / mass)
+             + p_vz * (-c.KD * v * vz * ex / mass - g * z / r + c.C * u[2] / mass)
+             - p_mass * c.b * norm_u;
+    }
+};
+
+// =============================== doubleIntegrator =============================================
+template <> struct Model<DOUBLE_INTEGRATOR> {
+    static constexpr int DIM = 6, N = 12, NP = 3, NCTRL = 3, DEFAULT_STEPS = 30;
+    struct Ctx { double umax, amax, muT; };
+    SOCP_DEV static void load(Ctx &c, const double *m, const double *) { c.umax = m[0]; c.amax = m[1]; c.muT = m[2]; }
+    // doubleIntegrator.cpp:218-259
+    SOCP_DEV static void control(const Ctx &c, double, const double *X, double *u) {
+        u[0] = -X[9] / c.amax; u[1] = -X[10] / c.amax; u[2] = -X[11] / c.amax;
+        double nu = sqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
+        if (nu > c.umax) {
+            u[0] = u[0] / nu * c.umax; u[1] = u[1] / nu * c.umax; u[2] = u[2] / nu * c.umax;
+        }
+    }
+    // doubleIntegrator.cpp:67-108
+    SOCP_DEV static void rhs(const Ctx &c, double t, const double *X, double *dX) {
+        double u[3];
+        control(c, t, X, u);
+        dX[0] = X[3]; dX[1] = X[4]; dX[2] = X[5];
+        dX[3] = c.amax * u[0]; dX[4] = c.amax * u[1]; dX[5] = c.amax * u[2];
+        dX[6] = 0; dX[7] = 0; dX[8] = 0;
+        dX[9] = -X[6]; dX[10] = -X[7]; dX[11] = -X[8];
+    }
+    // doubleIntegrator.cpp:264-300 (isJac == 0)
+    SOCP_DEV static double hamiltonian(const Ctx &c, double t, const double *X) {
+        double u[3];
+        control(c, t, X, u);
+        double nu = sqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
+        return c.muT + c.amax * c.amax * nu * nu / 2 + X[6] * X[3] + X[7] * X[4] + X[8] * X[5]
+             + c.amax * (X[9] * u[0] + X[10] * u[1] + X[11] * u[2]);
+    }
+};
+
+// =============================== covid19 ======================================================
+template <> struct Model<COVID19> {
+    static constexpr int DIM = 4, N = 8, NP = 8, NCTRL = 1, DEFAULT_STEPS = 1000;
+    struct Ctx { double R0, Tinf, Tinc, Npop, Imax, muI, umin, umax; };
+    SOCP_DEV static void load(Ctx &c, const double *m, const double *) {
+        c.R0 = m[0]; c.Tinf = m[1]; c.Tinc = m[2]; c.Npop = m[3]; c.Imax = m[4]; c.muI = m[5];
+        c.umin = m[6]; c.umax = m[7];
+    }
+    // covid19.cpp:98-129
+    SOCP_DEV static void control(const Ctx &c, double, const double *X, double *u) {
+        double v = (X[5] - X[4]) * X[0] * X[2] / c.Tinf / c.Npop * c.R0;
+        if (v <= c.umin) v = c.umin;
+        if (v >= c.umax) v = c.umax;
+        u[0] = v;
+    }
+    // covid19.cpp:53-95 -- the costate rows use R = X[3] where Rt was presumably meant; kept
+    SOCP_DEV static void rhs(const Ctx &c, double t, const double *X, double *dX) {
+        double S = X[0], E = X[1], I = X[2], R = X[3], pS = X[4], pE = X[5], pI = X[6], pR = X[7];
+        double u;
+        control(c, t, X, &u);
+        double Rt = c.R0 * (1 - u);
+        double Ipen = 0;
+        if (I >= c.Imax) Ipen = -c.muI * (I - c.Imax);
+        double inf = Rt / c.Tinf / c.Npop * S * I;
+        dX[0] = -inf;
+        dX[1] = inf - E / c.Tinc;
+        dX[2] = E / c.Tinc - I / c.Tinf;
+        dX[3] = I / c.Tinf;
+        dX[4] = (pS - pE) * R * I / c.Tinf / c.Npop;
+        dX[5] = (pE - pI) / c.Tinc;
+        dX[6] = (pS - pE) * R * S / c.Tinf / c.Npop + (pI - pR) / c.Tinf + Ipen;
+        dX[7] = 0;
+    }
+    // covid19.cpp:132-168
+    SOCP_DEV static double hamiltonian(const Ctx &c, double t, const double *X) {
+        double S = X[0], E = X[1], I = X[2], pS = X[4], pE = X[5], pI = X[6], pR = X[7];
+        double u;
+        control(c, t, X, &u);
+        double Rt = c.R0 * (1 - u);
+        double Ipen = 0;
+        if (I >= c.Imax) Ipen = c.muI * (I - c.Imax) * (I - c.Imax) / 2;
+        return u * u / 2 + Ipen + pS * (-Rt / c.Tinf / c.Npop * S * I)
+             + pE * (Rt / c.Tinf / c.Npop * S * I - E / c.Tinc) + pI * (E / c.Tinc - I / c.Tinf)
+             + pR * (I / c.Tinf);
+    }
+};
+
+// =============================== vtolUAV + obstacle map =======================================
+// obstacle.cpp:155-178 (Function / Gradient; the waypoint terms are commented out there),
+// :183-231 (penalty) and :236-316 (gradient; the ellipsoid gradient ignores z, :260-265).
+SOCP_DEV void obstacle_eval(double muObs, double phiObs, const double *pos, double *func, double *grad) {
+    double f = 0, g0 = 0, g1 = 0, g2 = 0;
+    const int n = c_num_obstacles;
+    for (int i = 0; i < n; ++i) {
+        const double *o = &c_obstacles[i * 7];
+        double type = o[0], x = o[1], y = o[2], z = o[3], radx = o[4], rady = o[5], radz = o[6];
+        if (type == 0) {
+            double hx = pos[0] - x, hy = pos[1] - y, hz = pos[2] - z;
+            double d = sqrt(hx * hx + hy * hy + hz * hz);
+            if (func) {
+                double rad = d / sqrt(hx * hx / radx / radx + hy * hy / rady / rady + hz * hz / radz / radz);
+                f = f + (1 - tanh((d - rad) / muObs)) / 2;
+            }
+            if (grad) {
+                double sq = sqrt(hx * hx / radx / radx + hy * hy / rady / rady);
+                double rad = d / sq;
+                double th = tanh((d - rad) / muObs);
+                double rho2 = (radx * radx - rady * rady) / (radx * radx * rady * rady) / sq / sq / sq;
+                g0 = g0 - hx / d * (1 - hy * hy * rho2) / muObs * (1 - th * th) / 2;
+                g1 = g1 - hy / d * (1 + hx * hx * rho2) / muObs * (1 - th * th) / 2;
+            }
+        } else if (type == 1) {
+            double dx = pos[0] - x, dy = pos[1] - y, dz = pos[2] - z;
+            double tx = tanh((fabs(dx) - radx) / muObs);
+            double ty = tanh((fabs(dy) - rady) / muObs);
+            double tz = tanh((fabs(dz) - radz) / muObs);
+            double ax = 1 - tx, ay = 1 - ty, az = 1 - tz;
+            f = f + ax * ay * az / 8;
+            if (grad) {
+                g0 = g0 - dx / fabs(dx) / muObs * (1 - tx * tx) * ay * az / 8;
+                g1 = g1 - dy / fabs(dy) / muObs * (1 - ty * ty) * ax * az / 8;
+                g2 = g2 - dz / fabs(dz) / muObs * (1 - tz * tz) * ax * ay / 8;
+            }
+        }
+    }
+    if (func) *func = phiObs * (isnan(f) ? 0.0 : f);
+    if (grad) {
+        grad[0] = phiObs * (isnan(g0) ? 0.0 : g0);
+        grad[1] = phiObs * (isnan(g1) ? 0.0 : g1);
+        grad[2] = phiObs * (isnan(g2) ? 0.0 : g2);
+    }
+}
+
+template <> struct Model<VTOL_UAV> {
+    static constexpr int DIM = 6, N = 12, NP = 13, NCTRL = 3, DEFAULT_STEPS = 100;
+    struct Ctx { double umax, amax, alphaT, alphaV, invSigma, Vd, ca, phiObs, muObs; };
+    SOCP_DEV static void load(Ctx &c, const double *m, const double *) {
+        c.umax = m[0]; c.amax = m[1]; c.alphaT = m[2]; c.alphaV = m[3]; c.invSigma = m[4];
+        c.Vd = m[5]; c.ca = m[6]; c.phiObs = m[9]; c.muObs = m[11];
+    }
+    // vtolUAV.cpp:110-148
+    SOCP_DEV static void control(const Ctx &c, double, const double *X, double *u) {
+        u[0] = -X[9] / c.amax; u[1] = -X[10] / c.amax; u[2] = -X[11] / c.amax;
+        double nu = sqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
+        if (nu > c.umax) {
+            u[0] = u[0] / nu * c.umax; u[1] = u[1] / nu * c.umax; u[2] = u[2] / nu * c.umax;
+        }
+    }
+    // vtolUAV.cpp:58-107
+    SOCP_DEV static void rhs(const Ctx &c, double t, const double *X, double *dX) {
+        double vx = X[3], vy = X[4], vz = X[5];
+        double p_x = X[6], p_y = X[7], p_z = X[8], p_vx = X[9], p_vy = X[10], p_vz = X[11];
+        double normV = sqrt(vx * vx + vy * vy + vz * vz);
+        double u[3], grad[3];
+        control(c, t, X, u);
+        obstacle_eval(c.muObs, c.phiObs, X, nullptr, grad);
+        dX[0] = vx; dX[1] = vy; dX[2] = vz;
+        dX[3] = c.amax * u[0] - c.ca * vx * normV;
+        dX[4] = c.amax * u[1] - c.ca * vy * normV;
+        dX[5] = c.amax * u[2] - c.ca * vz * normV;
+        dX[6] = 0 - grad[0]; dX[7] = 0 - grad[1]; dX[8] = 0 - grad[2];
+        dX[9] = -p_x + c.ca * (p_vx * (normV + vx * vx / normV) + p_vy * (vy * vx / normV) + p_vz * (vz * vx / normV)) - c.alphaV * vx / normV * (normV - c.Vd);
+        dX[10] = -p_y + c.ca * (p_vy * (normV + vy * vy / normV) + p_vx * (vx * vy / normV) + p_vz * (vz * vy / normV)) - c.alphaV * vy / normV * (normV - c.Vd);
+        dX[11] = -p_z + c.ca * (p_vz * (normV + vz * vz / normV) + p_vx * (vx * vz / normV) + p_vy * (vy * vz / normV)) - c.alphaV * vz / normV * (normV - c.Vd);
+    }
+    // vtolUAV.cpp:151-192
+    SOCP_DEV static double hamiltonian(const Ctx &c, double t, const double *X) {
+        double vx = X[3], vy = X[4], vz = X[5];
+        double p_x = X[6], p_y = X[7], p_z = X[8], p_vx = X[9], p_vy = X[10], p_vz = X[11];
+        double normV = sqrt(vx * vx + vy * vy + vz * vz);
+        double u[3], obs = 0;
+        control(c, t, X, u);
+        double nu = sqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
+        obstacle_eval(c.muObs, c.phiObs, X, &obs, nullptr);
+        return c.alphaT * 1 + c.alphaV / 2 * (normV - c.Vd) * (normV - c.Vd) + obs + c.amax * c.amax * nu * nu / 2
+             + p_x * vx + p_y * vy + p_z * vz
+             + (p_vx * (c.amax * u[0] - c.ca * vx * normV) + p_vy * (c.amax * u[1] - c.ca * vy * normV) + p_vz * (c.amax * u[2] - c.ca * vz * normV));
+    }
+};
+
+// =============================== interceptor ==================================================
+#define SOCP_R_EARTH 6378145.0      // interceptor.cpp:51
+#define SOCP_MU0 3.986e14           // interceptor.cpp:52
+#define SOCP_CHART_LIMIT 0.1        // interceptor.cpp:57
+#define SOCP_PI 3.14159265358979323846
+
+template <> struct Model<INTERCEPTOR> {
+    static constexpr int DIM = 6, N = 12, NP = 17, NCTRL = 2, DEFAULT_STEPS = 50;
+    struct Ctx {
+        double c0, hr, d0, eta, mprop, mempty, q, ve, alphamax, umax, mugft, muT, muV, muC;
+        int chart, stage;
+    };
+    SOCP_DEV static void load(Ctx &c, const double *m, const double *) {
+        c.c0 = m[0]; c.hr = m[1]; c.d0 = m[2]; c.eta = m[3]; c.mprop = m[4]; c.mempty = m[5];
+        c.q = m[6]; c.ve = m[7]; c.alphamax = m[8]; c.umax = m[9]; c.mugft = m[13]; c.muT = m[14];
+        c.muV = m[15]; c.muC = m[16];
+        c.chart = 1; c.stage = 0;
+    }
+    struct Tmp { double mass, c_max, d, r, g, ft; };
+    // the "temporary variables" block (interceptor.cpp:293-306) and ComputeMass (:984-999)
+    SOCP_DEV static void common(const Ctx &c, double t, double h, Tmp &k) {
+        double qm = c.stage * c.q * c.mugft;
+        double qm_mass = c.q * c.mugft;
+        double t1 = c.mprop / c.q;
+        k.mass = (c.stage == 1) ? c.mempty + c.mprop - qm_mass * t : c.mempty + c.mprop - qm_mass * t1;
+        double e = exp(-h / c.hr) * (c.mprop + c.mempty) / k.mass;
+        k.c_max = c.c0 * e;
+        k.d = c.d0 * e;
+        k.r = h + SOCP_R_EARTH;
+        k.g = SOCP_MU0 / k.r / k.r * c.mugft;
+        k.ft = c.ve * qm;
+    }
+    // interceptor.cpp:342-389 (chart 1) and :519-566 (chart 2): u and beta, with cos/sin(beta)
+    SOCP_DEV static void control_full(const Ctx &c, const Tmp &k, const double *X, double cang,
+                                      double &u, double &beta, double &sb, double &cb) {
+        double v = X[1], p_v = X[7], p_a = X[8], p_b = X[9];
+        double s = (c.chart == 1) ? 1.0 : -1.0;   // chart 2 flips the sign of the p_phi terms
+        beta = atan2(s * p_b, p_a * cang);
+        sincos(beta, &sb, &cb);
+        double am = c.alphamax / k.mass / v;
+        u = (p_a * (v * k.c_max * cb + k.ft * cb * am)
+             + s * p_b * (v * k.c_max * sb / cang + k.ft * sb / cang * am))
+            / (p_v * (2 * c.eta * k.c_max * v * v + k.ft * c.alphamax * c.alphamax / k.mass) - c.muC);
+        if (fabs(u) > c.umax) u = c.umax * u / fabs(u);
+    }
+    SOCP_DEV static void control(const Ctx &c, double t, const double *X, double *ctl) {
+        Tmp k;
+        common(c, t, X[0], k);
+        double u, beta, sb, cb;
+        control_full(c, k, X, cos(X[2]), u, beta, sb, cb);
+        ctl[0] = u; ctl[1] = beta;
+    }
+
+    // interceptor.cpp:275-339 (Model_1) and :445-516 (Model_2)
+    SOCP_DEV static void rhs(const Ctx &c, double t, const double *X, double *dX) {
+        double h = X[0], v = X[1], p_h = X[6], p_v = X[7], p_L = X[10], p_l = X[11];
+        Tmp k;
+        common(c, t, h, k);
+        double mass = k.mass, c_max = k.c_max, d = k.d, r = k.r, g = k.g, ft = k.ft, eta = c.eta, hr = c.hr;
+        double sL, cL;
+        sincos(X[4], &sL, &cL);
+        double tL = sL / cL;
+        double u, beta, sb, cb;
+        if (c.chart == 1) {
+            double p_gamma = X[8], p_chi = X[9];
+            double sg, cg, sc, cc;
+            sincos(X[2], &sg, &cg);
+            sincos(X[3], &sc, &cc);
+            control_full(c, k, X, cg, u, beta, sb, cb);
+            double sa, ca;
+            sincos(c.alphamax * u, &sa, &ca);
+            double dd = d + eta * c_max * u * u;
+            dX[0] = v * sg;
+            dX[1] = -dd * v * v - g * sg + ft * ca / mass;
+            dX[2] = v * c_max * u * cb - g / v * cg + ft * sa * cb / mass / v + v * cg / r;
+            dX[3] = v * c_max * u * sb / cg + ft * sa * sb / cg / mass / v + v * cg * tL * sc / r;
+            dX[4] = v * cg * cc / r;
+            dX[5] = v * cg * sc / cL / r;
+            dX[6] = -p_v / hr * dd * v * v - 2 * g / r * (p_gamma / v * cg + p_v * sg)
+                  + p_L * v * cg * cc / r / r + p_gamma * v * cg / r / r + p_gamma * v * c_max * u * cb / hr
+                  + p_l * v * cg * sc / cL / r / r + p_chi * v * cg * tL * sc / r / r + p_chi * v * c_max * u * sb / cg / hr;
+            dX[7] = -(p_L * cg * cc / r + p_l * cg * sc / cL / r + p_h * sg
+                      + p_gamma * (c_max * u * cb + g / v / v * cg - ft * sa * cb / mass / v / v + cg / r)
+                      + p_chi * (c_max * u * sb / cg - ft * sa * sb / cg / mass / v / v + cg * tL * sc / r)
+                      - p_v * 2 * dd * v);
+            dX[8] = v * (p_L * sg * cc / r + p_l * sg * sc / cL / r - p_h * cg)
+                  - g * (p_gamma / v * sg - p_v * cg)
+                  + p_gamma * v * sg / r + p_chi * v * sg * tL * sc / r
+                  - p_chi * (v * c_max * u * sb + ft * sa * sb / mass / v) * sg / cg / cg;
+            dX[9] = v * (p_L * cg * sc / r - p_l * cg * cc / cL / r - p_chi * cg * tL * cc / r);
+            dX[10] = -p_l * v * cg * sc * sL / cL / cL / r - p_chi * v * cg * (1 + tL * tL) * sc / r;
+            dX[11] = 0.0;
+        } else {
+            double p_theta = X[8], p_phi = X[9];
+            double st, ct, sp, cp;
+            sincos(X[2], &st, &ct);
+            sincos(X[3], &sp, &cp);
+            double tt = st / ct;
+            control_full(c, k, X, ct, u, beta, sb, cb);
+            double sa, ca;
+            sincos(c.alphamax * u, &sa, &ca);
+            double dd = d + eta * c_max * u * u;
+            double w1 = cp + sp * tL;                       // cos(phi) + sin(phi) tan(L)
+            double w2 = sp + tt * tt * (sp - tL * cp);      // sin(phi) + tan^2(theta)(sin(phi) - tan(L) cos(phi))
+            dX[0] = -v * ct * cp;
+            dX[1] = -dd * v * v + g * ct * cp + ft * ca / mass;
+            dX[2] = v * c_max * u * cb + v * st * w1 / r + (ft * sa * cb / (mass * v) - g * st * cp / v);
+            dX[3] = -v * c_max * u * sb / ct + v * ct * w2 / r - (ft * sa * sb / (mass * v * ct) + g * sp / (v * ct));
+            dX[4] = v * ct * sp / r;
+            dX[5] = v * st / (r * cL);
+            dX[6] = -p_v / hr * dd * v * v - 2 * g / r * (p_theta * st * cp / v + p_phi * sp / ct / v - p_v * ct * cp)
+                  + p_L * v * ct * sp / r / r + v * p_theta * st * w1 / r / r + p_theta * v * c_max * u * cb / hr
+                  + p_l * v * st / cL / r / r + v * p_phi * ct * w2 / r / r - p_phi * v * c_max * u * sb / ct / hr;
+            dX[7] = -(p_L * ct * sp / r + p_l * st / (r * cL) - p_h * ct * cp
+                      + p_theta * (c_max * u * cb + g / v / v * st * cp - ft * sa * cb / mass / v / v + st * w1 / r)
+                      + p_phi * (-c_max * u * sb / ct + g / v / v * sp / ct + ft * sa * sb / ct / mass / v / v + ct * w2 / r)
+                      - p_v * 2 * dd * v);
+            dX[8] = -v * (-p_L * st * sp / r + p_l * ct / (r * cL) + p_h * st * cp)
+                  - g * (-p_theta * ct * cp / v - p_phi * sp * tt / (v * ct) - p_v * st * cp)
+                  - p_theta * v * ct * w1 / r + p_phi * v * st * w2 / r
+                  - p_phi * v * ct * (2 * tt * (1 + tt * tt) * (sp - tL * cp)) / r
+                  - p_phi * (-v * c_max * u * sb - ft * sa * sb / mass / v) * tt / ct;
+            dX[9] = -v * (p_h * ct * sp + p_L * ct * cp / r)
+                  - g * (p_theta * st * sp / v - p_phi * cp / (v * ct) - p_v * ct * sp)
+                  - p_theta * (v * st * (-sp + cp * tL) / r)
+                  - p_phi * v * ct * (cp + tt * tt * (cp + tL * sp)) / r;
+            dX[10] = -p_l * v * st * tL / cL / r - v * (1 + tL * tL) * (p_theta * st * sp - p_phi * ct * cp * tt * tt) / r;
+            dX[11] = 0.0;
+        }
+    }
+
+    // interceptor.cpp:392-442 (Hamiltonian_1) and :569-619 (Hamiltonian_2)
+    SOCP_DEV static double hamiltonian(const Ctx &c, double t, const double *X) {
+        double h = X[0], v = X[1], p_h = X[6], p_v = X[7], p_a = X[8], p_b = X[9], p_L = X[10], p_l = X[11];
+        Tmp k;
+        common(c, t, h, k);
+        double mass = k.mass, c_max = k.c_max, d = k.d, r = k.r, g = k.g, ft = k.ft, eta = c.eta;
+        double sL, cL, s2, c2, s3, c3;
+        sincos(X[4], &sL, &cL);
+        sincos(X[2], &s2, &c2);
+        sincos(X[3], &s3, &c3);
+        double tL = sL / cL;
+        double u, beta, sb, cb;
+        control_full(c, k, X, c2, u, beta, sb, cb);
+        double sa, ca;
+        sincos(c.alphamax * u, &sa, &ca);
+        if (c.chart == 1) {
+            return p_L * v * c2 * c3 / r + p_l * v * c2 * s3 / cL / r + p_h * v * s2
+                 + p_a * (v * c_max * u * cb - g / v * c2 + ft * sa * cb / mass / v + v * c2 / r)
+                 + p_b * (v * c_max * u * sb / c2 + ft * sa * sb / c2 / mass / v + v * c2 * tL * s3 / r)
+                 - p_v * ((d + eta * c_max * u * u) * v * v + g * s2 - ft * ca / mass)
+                 + c.muC * u * u / 2;
+        }
+        double tt = s2 / c2;
+        return p_L * v * c2 * s3 / r + p_l * v * s2 / (r * cL) - p_h * v * c2 * c3
+             + p_a * (v * c_max * u * cb + v * s2 * (c3 + s3 * tL) / r + (ft * sa * cb / (mass * v) - g * s2 * c3 / v))
+             + p_b * (-v * c_max * u * sb / c2 + v * c2 * (s3 + tt * tt * (s3 - tL * c3)) / r - (ft * sa * sb / (mass * v * c2) + g * s3 / (v * c2)))
+             - p_v * ((d + eta * c_max * u * u) * v * v - g * c2 * c3 - ft * ca / mass)
+             + c.muC * u * u / 2;
+    }
+
+    // ---- chart handling (interceptor.cpp:622-841, 958-981) ----------------------------------
+    // Jacobians of the Cartesian embedding wrt chart 1 (gamma, chi) / chart 2 (theta, phi)
+    SOCP_DEV static void jac(int chart, double J[6][6], double L, double l, double r, double v, double a, double b) {
+        double sL, cL, sl, cl, sa, ca, sb, cb;
+        sincos(L, &sL, &cL); sincos(l, &sl, &cl); sincos(a, &sa, &ca); sincos(b, &sb, &cb);
+        J[0][0] = cL * cl; J[1][0] = -r * sL * cl; J[2][0] = -r * cL * sl; J[3][0] = 0; J[4][0] = 0; J[5][0] = 0;
+        J[0][1] = cL * sl; J[1][1] = -r * sL * sl; J[2][1] = r * cL * cl; J[3][1] = 0; J[4][1] = 0; J[5][1] = 0;
+        J[0][2] = sL; J[1][2] = r * cL; J[2][2] = 0; J[3][2] = 0; J[4][2] = 0; J[5][2] = 0;
+        J[0][3] = 0; J[0][4] = 0; J[0][5] = 0; J[2][5] = 0;
+        if (chart == 1) {       // a = gamma, b = chi
+            J[1][3] = (-cL * cl * ca * cb - sL * cl * sa) * v;
+            J[2][3] = (sL * sl * ca * cb - cl * ca * sb - cL * sl * sa) * v;
+            J[3][3] = (sL * cl * sa * cb + sl * sa * sb + cL * cl * ca) * v;
+            J[4][3] = (sL * cl * ca * sb - sl * ca * cb) * v;
+            J[5][3] = (-sL * cl * ca * cb - sl * ca * sb + cL * cl * sa) * v;
+            J[1][4] = (-cL * sl * ca * cb - sL * sl * sa) * v;
+            J[2][4] = (-sL * cl * ca * cb - sl * ca * sb + cL * cl * sa) * v;
+            J[3][4] = (sL * sl * sa * cb - cl * sa * sb + cL * sl * ca) * v;
+            J[4][4] = (sL * sl * ca * sb + cl * ca * cb) * v;
+            J[5][4] = (-sL * sl * ca * cb + cl * ca * sb + cL * sl * sa) * v;
+            J[1][5] = (-sL * ca * cb + cL * sa) * v;
+            J[3][5] = (-cL * sa * cb + sL * ca) * v;
+            J[4][5] = -cL * ca * sb * v;
+            J[5][5] = (cL * ca * cb + sL * sa) * v;
+        } else {                // a = theta, b = phi
+            J[1][3] = (-cL * cl * ca * sb + sL * cl * ca * cb) * v;
+            J[2][3] = (sL * sl * ca * sb - cl * sa + cL * sl * ca * cb) * v;
+            J[3][3] = (sL * cl * sa * sb - sl * ca + cL * cl * sa * cb) * v;
+            J[4][3] = (-sL * cl * ca * cb + cL * cl * ca * sb) * v;
+            J[5][3] = (-sL * cl * ca * sb - sl * sa - cL * cl * ca * cb) * v;
+            J[1][4] = (-cL * sl * ca * sb + sL * sl * ca * cb) * v;
+            J[2][4] = (-sL * cl * ca * sb - sl * sa - cL * cl * ca * cb) * v;
+            J[3][4] = (sL * sl * sa * sb + cl * ca + cL * sl * sa * cb) * v;
+            J[4][4] = (-sL * sl * ca * cb + cL * sl * ca * sb) * v;
+            J[5][4] = (-sL * sl * ca * sb + cl * sa - cL * sl * ca * cb) * v;
+            J[1][5] = (-sL * ca * sb - cL * ca * cb) * v;
+            J[3][5] = (-cL * sa * sb + sL * sa * cb) * v;
+            J[4][5] = (cL * ca * cb + sL * ca * sb) * v;
+            J[5][5] = (cL * ca * sb - sL * ca * cb) * v;
+        }
+    }
+    // 6x6 partial-pivot LU solve (stands in for Eigen's lu().solve(), interceptor.cpp:715,829)
+    __device__ static void lu6_solve(double A[6][6], const double *b, double *x) {
+        int piv[6];
+        for (int i = 0; i < 6; ++i) piv[i] = i;
+        for (int k = 0; k < 6; ++k) {
+            int pr = k;
+            double best = fabs(A[k][k]);
+            for (int i = k + 1; i < 6; ++i)
+                if (fabs(A[i][k]) > best) { best = fabs(A[i][k]); pr = i; }
+            if (pr != k) {
+                for (int j = 0; j < 6; ++j) { double t = A[k][j]; A[k][j] = A[pr][j]; A[pr][j] = t; }
+                int ti = piv[k]; piv[k] = piv[pr]; piv[pr] = ti;
+            }
+            for (int i = k + 1; i < 6; ++i) {
+                A[i][k] /= A[k][k];
+                for (int j = k + 1; j < 6; ++j) A[i][j] -= A[i][k] * A[k][j];
+            }
+        }
+        double y[6];
+        for (int i = 0; i < 6; ++i) y[i] = b[piv[i]];
+        for (int i = 0; i < 6; ++i)
+            for (int j = 0; j < i; ++j) y[i] -= A[i][j] * y[j];
+        for (int i = 5; i >= 0; --i) {
+            for (int j = i + 1; j < 6; ++j) y[i] -= A[i][j] * y[j];
+            y[i] /= A[i][i];
+        }
+        for (int i = 0; i < 6; ++i) x[i] = y[i];
+    }
+    // ConversionState12 (from == 1) / ConversionState21 (from == 2), in place
+    __device__ static void convert(int from, double *X) {
+        const double eps = 1e-18;
+        double v = X[1], a = X[2], b = X[3], L = X[4], l = X[5];
+        double r = X[0] + SOCP_R_EARTH;
+        double na, nb;
+        if (from == 1) {                     // (gamma, chi) -> (theta, phi)
+            double gamma = a, chi = b;
+            if (gamma == SOCP_PI / 2.0) { na = 0; nb = -SOCP_PI; }
+            else if (gamma == -SOCP_PI / 2.0) { na = 0; nb = 0; }
+            else {
+                double sg = sin(gamma), cg = cos(gamma), sc = sin(chi), cc = cos(chi);
+                na = acos(sqrt(sg * sg + cg * cg * cc * cc));
+                if (cg * sc < 0) na = -na;
+                double ct = cos(na);
+                double sinPhi = cg * cc / ct;
+                if (fabs(sinPhi) < eps && sg / ct < 0) nb = 0;
+                else if (fabs(sinPhi) < eps && sg / ct > 0) nb = -SOCP_PI;
+                else if (sinPhi > 0) nb = acos(-sg / ct);
+                else nb = -acos(-sg / ct);
+            }
+        } else {                             // (theta, phi) -> (gamma, chi)
+            double theta = a, phi = b;
+            if (theta == SOCP_PI / 2.0) { na = 0; nb = SOCP_PI / 2.0; }
+            else if (theta == -SOCP_PI / 2.0) { na = 0; nb = -SOCP_PI / 2.0; }
+            else {
+                double st = sin(theta), ct = cos(theta), sp = sin(phi), cp = cos(phi);
+                na = acos(sqrt(st * st + ct * ct * sp * sp));
+                if (ct * cp > 0) na = -na;
+                double cg = cos(na);
+                double sinChi = st / cg;
+                if (fabs(sinChi) < eps && sp * ct / cg > 0) nb = 0;
+                else if (fabs(sinChi) < eps && sp * ct / cg < 0) nb = -SOCP_PI;
+                else if (sinChi > 0) nb = acos(sp * ct / cg);
+                else nb = -acos(sp * ct / cg);
+            }
+        }
+        double Jf[6][6], Jt[6][6];
+        jac(from, Jf, L, l, r, v, a, b);
+        jac(3 - from, Jt, L, l, r, v, na, nb);
+        double pf[6] = {X[6], X[10], X[11], X[8], X[9], X[7]}, tmp[6], pt[6];
+        lu6_solve(Jf, pf, tmp);
+        for (int i = 0; i < 6; ++i) {
+            double s = 0;
+            for (int j = 0; j < 6; ++j) s += Jt[i][j] * tmp[j];
+            pt[i] = s;
+        }
+        X[2] = na; X[3] = nb;
+        X[6] = pt[0]; X[7] = pt[5]; X[8] = pt[3]; X[9] = pt[4]; X[10] = pt[1]; X[11] = pt[2];
+    }
+    // SetChart (interceptor.cpp:958-981)
+    SOCP_DEV static void set_chart(Ctx &c, double *X) {
+        if (fabs(cos(X[2])) >= SOCP_CHART_LIMIT) return;
+        convert(c.chart, X);
+        c.chart = 3 - c.chart;
+    }
+};
+
+}  // namespace socp

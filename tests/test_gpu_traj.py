@@ -1,0 +1,114 @@
+"""GPU parity of the RK4 trajectory kernel (socp_traj_batch) and of the point evaluations
+(socp_point_batch) against the golden vectors of the reference and against the oracle.
+
+Tolerance (BASELINE.json north_star / SURVEY.md section 8d): fixed-step RK4 trajectories agree to
+<= 1e-12 norm-relative, and <= 1e-12 component-relative for components above 1e-6 * |X|_inf.
+"""
+import numpy as np
+import pytest
+
+import scenarios as S
+from golden_util import golden, unhex
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+@pytest.fixture(scope="module")
+def eng():
+    import socp_b200 as sb
+    e = sb.Engine(0)
+    o = S.VTOL_OBSTACLES
+    e.set_obstacles(o["type"], o["pos"], o["rad"])
+    return e
+
+
+def check_traj(got, want, what, tol=TOL):
+    got, want = np.asarray(got), np.asarray(want)
+    scale = np.max(np.abs(want))
+    norm_rel = np.max(np.abs(got - want)) / scale
+    big = np.abs(want) >= 1e-6 * scale
+    comp_rel = np.max(np.abs(got - want)[big] / np.abs(want)[big]) if np.any(big) else 0.0
+    assert norm_rel <= tol and comp_rel <= tol, "%s: norm-rel %.3e comp-rel %.3e" % (what, norm_rel, comp_rel)
+    return norm_rel, comp_rel
+
+
+def test_golden_trajectories(eng):
+    worst = 0.0
+    for k, e in enumerate(golden()["traj"]):
+        sw = unhex(e["sw"])
+        got = eng.traj_batch(e["model"], unhex(e["mparams"]), unhex(e["t0"]), unhex(e["X0"])[None, :],
+                             unhex(e["tf"]), e["steps"], sw=None if sw is None else sw[None, :])
+        # the KD=310 trivial-guess Goddard trajectory is ill-conditioned (costates grow to 1e8);
+        # SURVEY 8c measured 2e-13 from FMA contraction alone on it
+        nr, cr = check_traj(got[0], unhex(e["Xf"]), "golden traj %d (model %d)" % (k, e["model"]))
+        worst = max(worst, nr, cr)
+    print("worst golden trajectory error %.3e" % worst)
+
+
+def test_golden_points(eng):
+    for k, e in enumerate(golden()["points"]):
+        sw = unhex(e["sw"])
+        rhs, ctl, H = eng.point_batch(e["model"], unhex(e["mparams"]), unhex(e["t"]), unhex(e["X"])[None, :],
+                                      sw=None if sw is None else sw[None, :])
+        want = unhex(e["rhs"])
+        scale = np.max(np.abs(want))
+        assert np.max(np.abs(rhs[0] - want)) <= 1e-13 * scale, "rhs %d model %d" % (k, e["model"])
+        wc = unhex(e["control"])
+        assert np.max(np.abs(ctl[0, :wc.size] - wc)) <= 1e-13 * max(1.0, np.max(np.abs(wc)))
+        wH = unhex(e["H"])
+        assert abs(H[0] - wH) <= 1e-12 * max(abs(wH), scale, 1.0)
+
+
+@pytest.mark.parametrize("model", range(5))
+def test_random_batch_vs_oracle(eng, oracle_lib, model):
+    from backends import OracleBackend
+    ora = OracleBackend()
+    rng = np.random.default_rng(20260200 + model)
+    base = {S.GODDARD: S.GODDARD_XI, S.DI: np.r_[np.zeros(6), 0.01 * np.ones(6)], S.COVID19: S.COVID_XI,
+            S.VTOL: np.array([20, 8, 5, 0.3, 0.2, 0.1, -0.03, 0.013, -0.003, -0.29, 0.1, -0.03]),
+            S.INTERCEPTOR: np.array(S.INTERCEPTOR_INIT_XI + [0.01, -1, 0.5, 0.2, 100., 50.])}[model]
+    mp = np.array(S.DEFAULTS[model])
+    if model == S.GODDARD:
+        mp[6], mp[2] = 1.0, 0.0
+    tf = {S.GODDARD: 0.05, S.DI: 8.0, S.COVID19: 20.0, S.VTOL: 5.0, S.INTERCEPTOR: 25.0}[model]
+    B = 300
+    X0 = base * (1.0 + 0.05 * rng.uniform(-1, 1, size=(B, base.size))) + 1e-3 * rng.uniform(-1, 1, size=(B, base.size))
+    got = eng.traj_batch(model, mp, 0.0, X0, tf)
+    for k in range(0, B, 7):
+        check_traj(got[k], ora.traj(model, mp, 0.0, X0[k], tf), "model %d item %d" % (model, k))
+
+
+def test_ragged_and_empty(eng):
+    mp = np.array(S.DEFAULTS[S.GODDARD]); mp[6] = 1.0
+    # empty batch
+    out = eng.traj_batch(S.GODDARD, mp, 0.0, np.zeros((0, 14)), 0.1)
+    assert out.shape == (0, 14)
+    # tf <= t0 performs zero steps (odeTools.cpp:135): the state is returned unchanged
+    X0 = np.tile(S.GODDARD_XI, (5, 1))
+    out = eng.traj_batch(S.GODDARD, mp, np.array([0.1, 0.1, 0.0, 0.2, 0.0]), X0, np.array([0.1, 0.05, 0.1, 0.1, 0.0]))
+    assert np.array_equal(out[0], X0[0]) and np.array_equal(out[1], X0[1]) and np.array_equal(out[3], X0[3])
+    assert np.array_equal(out[4], X0[4]) and not np.array_equal(out[2], X0[2])
+    # a batch that is not a multiple of the block size
+    out = eng.traj_batch(S.GODDARD, mp, 0.0, np.tile(S.GODDARD_XI, (129, 1)), 0.1)
+    assert np.all(out == out[0])
+
+
+def test_full_size_properties(eng):
+    """BASELINE-size batch (1e5 Goddard trajectories): size-independent properties."""
+    B = 100000
+    Xi, _ = S.goddard_batch_inputs(B)
+    mp = np.array(S.DEFAULTS[S.GODDARD]); mp[6], mp[2] = 1.0, 0.0
+    eng.reset_stats()
+    a = eng.traj_batch(S.GODDARD, mp, 0.0, Xi, 0.1)
+    assert eng.stats()["rk4_steps"] == 10 * B
+    # determinism and permutation equivariance
+    perm = np.random.default_rng(0).permutation(B)
+    b = eng.traj_batch(S.GODDARD, mp, 0.0, Xi[perm], 0.1)
+    assert np.array_equal(a[perm], b)
+    # semigroup property of the fixed-step integrator: 10 steps = 5 steps + 5 steps
+    mid = eng.traj_batch(S.GODDARD, mp, 0.0, Xi, 0.05, step_nbr=5)
+    c = eng.traj_batch(S.GODDARD, mp, 0.05, mid, 0.1, step_nbr=5)
+    assert np.max(np.abs(a - c) / np.max(np.abs(a), axis=1, keepdims=True)) <= 1e-13
+    # mass only decreases, and by at most b * u_max * tf
+    assert np.all(a[:, 6] <= Xi[:, 6]) and np.all(a[:, 6] >= Xi[:, 6] - 7.0 * 1.0 * 0.1 - 1e-12)
