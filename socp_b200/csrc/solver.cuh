@@ -1,8 +1,879 @@
-// placeholder, replaced by the batched solver
+// socp_b200/csrc/solver.cuh -- batched shooting residual, FD Jacobian and Powell-hybrid solve.
+//
+// Lock-step reverse-communication design: every problem of the batch carries its own MINPACK
+// `hybrd` state (phase, trust radius, counters, QR factors) in HBM.  One ROUND is two kernels:
+//
+//   integrate_worklist   one thread per (problem, segment[, perturbed column]) work item: RK4 over
+//                        one shooting segment with the state in registers.  A residual request is
+//                        M items, a forward-difference Jacobian request is 2*dim*M + nfree*M items
+//                        (only the segment a perturbed unknown can influence is re-integrated; the
+//                        other entries of that column are exactly zero in the reference too).
+//   advance              one thread group per problem: assemble the residual / Jacobian from the
+//                        segment end points (boundary functions, continuity, free-time conditions),
+//                        run the hybrd state machine up to its next function evaluation and append
+//                        the problem to the next round's work list -- or retire it (converged /
+//                        failed), which is the convergence mask.
+//
+// Restates: shooting::ShootingFunction (src/socp/shooting.cpp:918-993), ComputeTimeLine
+// (:1579-1617), MultipleShootingFunction (:1511-1576, isJac == 0), the boundary functions of
+// model.hpp:90-255 with the model overrides (interceptor.cpp:223-272, vtolUAV.cpp:223-283,
+// goddard.cpp:343-370), and MINPACK hybrd/fdjac1/qrfac/qform/dogleg/r1updt/r1mpyq as called from
+// shooting.cpp:803-826 (ml = mu = n-1, epsfcn = 1e-15, mode = 1, factor = 1).
 #pragma once
+#include <cuda_runtime.h>
+#include <float.h>
+#include "../../include/socp_b200.h"
+#include "models.cuh"
+#include "integrate.cuh"
+
 namespace socp {
-struct SolverWorkspace {
-    void release() {}
-    double bytes() const { return 0; }
+
+enum { PH_IDLE = 0, PH_F0 = 1, PH_JAC = 2, PH_TRIAL = 3 };
+enum { RUN_SOLVE = 0, RUN_RESIDUAL = 1, RUN_FDJAC = 2 };
+// per-problem integer state
+enum { I_PHASE = 0, I_ITER, I_NCSUC, I_NCFAIL, I_NSLOW1, I_NSLOW2, I_JEVAL, I_NFEV, I_INFO, I_BASE, I_COUNT = 12 };
+// per-problem scalar state
+enum { D_DELTA = 0, D_XNORM, D_FNORM, D_PNORM, D_COUNT = 4 };
+
+struct SolverDev {
+    // shape
+    int model_id, dim, N, M, S, P, nfree, np, nJ, REC, LR;
+    int mode_t[SOCP_MAX_NODES];
+    int mode_X[SOCP_MAX_NODES][SOCP_MAX_DIM];
+    const int *jac_col, *jac_seg;          // [nJ] work item -> (column, segment)
+    const int *col_item0, *col_nseg;       // [P] first item of a column; 1 or M segments
+    // problem data
+    long B;
+    const double *mparams, *time, *Xb;
+    // solver settings
+    double xtol, epsfcn, factor;
+    int maxfev, run_mode;
+    // persistent state
+    double *x, *xe, *fvec, *diag, *qtf, *wa1, *wa2, *wa3, *wa4, *scr, *fjac, *r, *ends, *jends, *dstate;
+    int *istate;
+    // work lists, double buffered: list[2][2][B], count[2][2]
+    int *lists;
+    int *counts;
+    unsigned long long *counters;
 };
+
+#define EPSMCH DBL_EPSILON
+
+// ---- group helpers ---------------------------------------------------------------------------
+template <int G> SOCP_DEV void gsync() { if (G == 32) __syncwarp(); else __syncthreads(); }
+
+// sum over the group; the result is identical in every thread (fixed reduction tree)
+template <int G> SOCP_DEV double gsum(double v, double *red) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    if (G == 32) return v;
+    const int w = threadIdx.x >> 5;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[w] = v;
+    __syncthreads();
+    double t = 0;
+#pragma unroll
+    for (int k = 0; k < G / 32; ++k) t += red[k];
+    return t;
 }
+
+// MINPACK enorm, sequential (used for the rare badly-scaled case)
+__device__ __noinline__ double enorm_seq(int n, const double *x, int stride) {
+    const double rdwarf = 3.834e-20, rgiant = 1.304e19;
+    double s1 = 0., s2 = 0., s3 = 0., x1max = 0., x3max = 0.;
+    const double agiant = rgiant / (double)n;
+    for (int i = 0; i < n; ++i) {
+        double xabs = fabs(x[(long)i * stride]);
+        if (xabs > rdwarf && xabs < agiant) s2 += xabs * xabs;
+        else if (xabs <= rdwarf) {
+            if (xabs > x3max) { double q = x3max / xabs; s3 = 1. + s3 * (q * q); x3max = xabs; }
+            else if (xabs != 0.) { double q = xabs / x3max; s3 += q * q; }
+        } else {
+            if (xabs > x1max) { double q = x1max / xabs; s1 = 1. + s1 * (q * q); x1max = xabs; }
+            else { double q = xabs / x1max; s1 += q * q; }
+        }
+    }
+    if (s1 != 0.) return x1max * sqrt(s1 + (s2 / x1max) / x1max);
+    if (s2 != 0.) {
+        if (s2 >= x3max) return sqrt(s2 * (1. + (x3max / s2) * (x3max * s3)));
+        return sqrt(x3max * ((s2 / x3max) + (x3max * s3)));
+    }
+    return x3max * sqrt(s3);
+}
+
+// Euclidean norm of x[0..n) over the group: plain sum of squares when every component is in
+// MINPACK's "intermediate" range (the normal case), the scaled sequential algorithm otherwise.
+template <int G> SOCP_DEV double enorm_g(int n, const double *x, double *red) {
+    const double rdwarf = 3.834e-20, rgiant = 1.304e19;
+    const double agiant = rgiant / (double)n;
+    const int tid = threadIdx.x % G;
+    double s2 = 0., odd = 0.;
+    for (int i = tid; i < n; i += G) {
+        double xabs = fabs(x[i]);
+        if (xabs > rdwarf && xabs < agiant) s2 += xabs * xabs;
+        else if (xabs != 0.) odd += 1.;
+    }
+    s2 = gsum<G>(s2, red);
+    odd = gsum<G>(odd, red);
+    if (odd != 0. || !(s2 == s2)) return enorm_seq(n, x, 1);
+    return sqrt(s2);
+}
+
+// ---- time line (shooting.cpp:1579-1617) --------------------------------------------------------
+// Node times from the fixed times and the FREE-time unknowns, linear interpolation for CONTINUOUS
+// nodes.  xfree(k) returns the k-th free-time unknown (already perturbed if needed).
+// sw[2] receives the first two FREE interior times (SwitchingTimesUpdate, goddard.cpp:373).
+template <class XF>
+SOCP_DEV void timeline_all(const SolverDev &D, const double *time_b, XF xfree, double *tl, double *sw) {
+    int k = 0, cur = 0, nsw = 0;
+    for (int j = 0; j <= D.M; ++j) {
+        const int m = D.mode_t[j];
+        if (m == SOCP_FIXED || m == SOCP_FREE) {
+            double tj;
+            if (m == SOCP_FIXED) tj = time_b[j];
+            else {
+                tj = xfree(k++);
+                if (j < D.M && nsw < 2) sw[nsw++] = tj;
+            }
+            tl[j] = tj;
+            for (int q = cur + 1; q < j; ++q) tl[q] = tl[cur] + (q - cur) * (tl[j] - tl[cur]) / (j - cur);
+            cur = j;
+        }
+    }
+}
+// the two node times of segment s without materialising the whole line
+template <class XF>
+SOCP_DEV void timeline_pair(const SolverDev &D, const double *time_b, XF xfree, int s, double &t1, double &t2, double *sw) {
+    int k = 0, cur = 0, nsw = 0;
+    double tcur = 0;
+    t1 = t2 = 0;
+    for (int j = 0; j <= D.M; ++j) {
+        const int m = D.mode_t[j];
+        if (m == SOCP_FIXED || m == SOCP_FREE) {
+            double tj;
+            if (m == SOCP_FIXED) tj = time_b[j];
+            else {
+                tj = xfree(k++);
+                if (j < D.M && nsw < 2) sw[nsw++] = tj;
+            }
+            if (s > cur && s < j) t1 = tcur + (s - cur) * (tj - tcur) / (j - cur);
+            else if (s == j) t1 = tj;
+            if (s + 1 > cur && s + 1 < j) t2 = tcur + (s + 1 - cur) * (tj - tcur) / (j - cur);
+            else if (s + 1 == j) t2 = tj;
+            cur = j;
+            tcur = tj;
+        }
+    }
+}
+
+// MINPACK fdjac1 step for unknown value v
+SOCP_DEV double fd_step(double v, double epsfcn) {
+    double eps = sqrt(fmax(epsfcn, EPSMCH));
+    double h = eps * fabs(v);
+    if (h == 0.) h = eps;
+    return h;
+}
+
+// ---- kernel 1: integrate every requested shooting segment --------------------------------------
+template <int MODEL>
+__global__ void __launch_bounds__(128)
+integrate_worklist(SolverDev D, int cur) {
+    typedef Model<MODEL> M;
+    constexpr int N = M::N;
+    const int nres = D.counts[cur * 2 + 0], njac = D.counts[cur * 2 + 1];
+    const int *res_list = D.lists + (size_t)(cur * 2 + 0) * D.B;
+    const int *jac_list = D.lists + (size_t)(cur * 2 + 1) * D.B;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {       // next-next round's counters
+        D.counts[(1 - cur) * 2 + 0] = 0;
+        D.counts[(1 - cur) * 2 + 1] = 0;
+    }
+    const long total = (long)nres * D.M + (long)njac * D.nJ;
+    int steps = 0;
+    for (long w = (long)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += (long)gridDim.x * blockDim.x) {
+        long b;
+        int s, col;
+        double *out;
+        if (w < (long)nres * D.M) {
+            b = res_list[w / D.M];
+            s = (int)(w % D.M);
+            col = -1;
+            const int trial = 1 - D.istate[b * I_COUNT + I_BASE];
+            out = D.ends + ((b * 2 + trial) * D.M + s) * D.REC;
+        } else {
+            const long w2 = w - (long)nres * D.M;
+            b = jac_list[w2 / D.nJ];
+            const int k = (int)(w2 % D.nJ);
+            col = D.jac_col[k];
+            s = D.jac_seg[k];
+            out = D.jends + (b * D.nJ + k) * D.REC;
+        }
+        const double *xe = D.xe + b * D.P;
+        const double h = (col >= 0) ? fd_step(xe[col], D.epsfcn) : 0.0;
+        const int nm = N * D.M;
+        double t1, t2, sw[2] = {0.0227, 0.08};
+        timeline_pair(D, D.time + b * (D.M + 1),
+                      [&](int k) { int idx = nm + k; return xe[idx] + ((idx == col) ? h : 0.0); }, s, t1, t2, sw);
+        typename M::Ctx c;
+        M::load(c, D.mparams + b * M::NP, sw);
+        double X[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) X[i] = xe[N * s + i];
+        if (col >= 0 && col < nm && col / N == s) {
+            const int kk = col - N * s;
+#pragma unroll
+            for (int i = 0; i < N; ++i) if (i == kk) X[i] += h;
+        }
+        steps += compute_traj<MODEL>(c, X, t1, t2, D.S);
+#pragma unroll
+        for (int i = 0; i < N; ++i) out[i] = X[i];
+        int chart, stage;
+        get_chart_stage<MODEL>(c, chart, stage);
+        out[N] = (double)chart;
+        out[N + 1] = (double)stage;
+    }
+    count_steps(D.counters, steps);
+}
+
+// ---- residual assembly (one thread) ------------------------------------------------------------
+// Emits every entry of F(xe + h e_col) (col < 0: the base point) through emit(i, value).
+template <int MODEL, class EMIT>
+__device__ void assemble(const SolverDev &D, long b, int col, double h, const double *base_ends,
+                         const double *jends_b, EMIT emit) {
+    typedef Model<MODEL> M;
+    constexpr int N = M::N, n = M::DIM;
+    const double *xe = D.xe + b * D.P;
+    const double *Xb = D.Xb + b * (D.M + 1) * n;
+    const double *mp = D.mparams + b * M::NP;
+    auto xv = [&](int idx) { return xe[idx] + ((idx == col) ? h : 0.0); };
+    auto rec = [&](int s) -> const double * {
+        if (col < 0) return base_ends + s * D.REC;
+        if (D.col_nseg[col] == 1) {
+            const int seg0 = D.jac_seg[D.col_item0[col]];
+            return (s == seg0) ? jends_b + (size_t)D.col_item0[col] * D.REC : base_ends + s * D.REC;
+        }
+        return jends_b + (size_t)(D.col_item0[col] + s) * D.REC;
+    };
+    double tl[SOCP_MAX_NODES + 1], sw[2] = {0.0227, 0.08};
+    const int nm = N * D.M;
+    timeline_all(D, D.time + b * (D.M + 1), [&](int k) { return xv(nm + k); }, tl, sw);
+    typename M::Ctx c;
+    M::load(c, mp, sw);
+    int nbr = nm;
+    double X1[N], Xtf[N], Xp[N];
+    for (int i = 0; i < D.M; ++i) {
+        const double t2 = tl[i + 1];
+        const double *e = rec(i);
+#pragma unroll
+        for (int k = 0; k < N; ++k) { Xtf[k] = e[k]; X1[k] = xv(N * i + k); }
+        set_chart_stage<MODEL>(c, (int)e[N], (int)e[N + 1]);
+        const int index = N * (i + 1);
+        if (i == 0) {
+            // model::InitialFunction (model.hpp:196-213) / InitialHFunction (:239-255)
+            for (int k = 0; k < n; ++k)
+                emit(k, (D.mode_X[0][k] == SOCP_FREE) ? X1[k + n] : X1[k] - Xb[k]);
+            if (D.mode_t[0] != SOCP_FIXED) {
+                emit(nm, M::hamiltonian(c, tl[0], X1));
+                nbr += 1;
+            }
+        }
+        if (i < D.M - 1) {
+#pragma unroll
+            for (int k = 0; k < N; ++k) Xp[k] = xv(index + k);
+            if (D.mode_t[i + 1] == SOCP_FREE) {
+                // SwitchingTimesFunction: H(X) - H(Xp) (model.hpp:299-305); goddard: H(X) (goddard.cpp:343-370)
+                double Hx = M::hamiltonian(c, t2, Xtf);
+                if (MODEL != GODDARD) Hx -= M::hamiltonian(c, t2, Xp);
+                emit(nbr, Hx);
+                nbr += 1;
+            }
+            // shooting::MultipleShootingFunction (shooting.cpp:1511-1576, isJac == 0)
+            const double *Xd = Xb + (i + 1) * n;
+            for (int k = 0; k < n; ++k) {
+                const int m = D.mode_X[i + 1][k];
+                if (m == SOCP_FIXED) {
+                    emit(index + k, Xtf[k] - Xd[k]);
+                    emit(index + k + n, Xp[k] - Xd[k]);
+                } else if (m == SOCP_FREE) {
+                    // model::SwitchingStateFunction: empty by default (model.hpp:339);
+                    // vtolUAV.cpp:273-283 adds the waypoint penalty to the costate jump
+                    if (MODEL == VTOL_UAV) {
+                        emit(index + k, Xtf[k] - Xp[k]);
+                        emit(index + k + n, (Xtf[k + n] - Xp[k + n]) - mp[4] * (Xtf[k] - Xd[k]));
+                    } else {
+                        emit(index + k, 0.0);
+                        emit(index + k + n, 0.0);
+                    }
+                } else {
+                    emit(index + k, Xtf[k] - Xp[k]);
+                    emit(index + k + n, Xtf[k + n] - Xp[k + n]);
+                }
+            }
+        }
+        if (i == D.M - 1) {
+            // model::FinalFunction (model.hpp:90-103) and overrides interceptor.cpp:223-245,
+            // vtolUAV.cpp:223-241; FinalHFunction adds H (+ muT for the interceptor, :270)
+            const double *Xf = Xb + D.M * n;
+            for (int k = 0; k < n; ++k) {
+                double f;
+                if (D.mode_X[D.M][k] == SOCP_FREE) {
+                    f = Xtf[k + n];
+                    if (MODEL == INTERCEPTOR && k == 1) f = Xtf[k + n] + mp[15];
+                    if (MODEL == VTOL_UAV) {
+                        const int nWP_tot = (int)mp[7], nWP = (int)mp[8];
+                        f = Xtf[k + n] - mp[4] * (nWP_tot - nWP) * (Xtf[k] - Xf[k]) - 0.02 * (Xtf[k] - Xf[k]);
+                    }
+                } else {
+                    f = Xtf[k] - Xf[k];
+                    if (MODEL == INTERCEPTOR) {
+                        if (k == 0) f = f / mp[1];
+                        if (k == 3 && fabs(cos(Xf[2])) < 1e-5) f = Xtf[k + n];
+                    }
+                }
+                emit(k + n, f);
+            }
+            if (D.mode_t[D.M] != SOCP_FIXED) {
+                double H = M::hamiltonian(c, t2, Xtf);
+                if (MODEL == INTERCEPTOR) H += mp[14];
+                emit(nbr, H);
+                nbr += 1;
+            }
+        }
+    }
+}
+
+// ---- MINPACK linear algebra on a thread group --------------------------------------------------
+// Matrices are column-major with leading dimension n (cminpack convention); r is the packed upper
+// triangle stored by rows.  Every routine starts and ends with a group barrier.
+
+// qrfac (no pivoting) fused with "qtf = Q^T fvec" (the Householder reflections are applied to
+// qtf as one more column); rdiag/acnorm as in MINPACK.
+template <int G>
+__device__ void qrfac_g(int n, double *a, double *rdiag, double *acnorm, double *qtf, double *red) {
+    const int tid = threadIdx.x % G;
+    gsync<G>();
+    for (int j = tid; j < n; j += G) {                 // column norms
+        const double *cj = a + (size_t)j * n;
+        double s2 = 0;
+        bool odd = false;
+        for (int i = 0; i < n; ++i) {
+            double v = fabs(cj[i]);
+            if (v > 3.834e-20 && v < 1.304e19 / n) s2 += v * v;
+            else if (v != 0.) odd = true;
+        }
+        acnorm[j] = odd ? enorm_seq(n, cj, 1) : sqrt(s2);
+    }
+    gsync<G>();
+    for (int j = 0; j < n; ++j) {
+        double *cj = a + (size_t)j * n;
+        double ajnorm = enorm_g<G>(n - j, cj + j, red);
+        if (ajnorm != 0.) {
+            if (cj[j] < 0.) ajnorm = -ajnorm;
+            gsync<G>();
+            for (int i = j + tid; i < n; i += G) {
+                double v = cj[i] / ajnorm;
+                if (i == j) v += 1.;
+                cj[i] = v;
+            }
+            gsync<G>();
+            const double ajj = cj[j];
+            for (int k = j + 1 + tid; k <= n; k += G) {  // remaining columns, and qtf as column n
+                double *ck = (k < n) ? a + (size_t)k * n : qtf;
+                double sum = 0.;
+                for (int i = j; i < n; ++i) sum += cj[i] * ck[i];
+                const double temp = sum / ajj;
+                for (int i = j; i < n; ++i) ck[i] -= temp * cj[i];
+            }
+        }
+        if (tid == 0) rdiag[j] = -ajnorm;
+        gsync<G>();
+    }
+}
+
+// copy R into packed storage (upper triangle by rows), diagonal from rdiag
+template <int G>
+__device__ void pack_r_g(int n, const double *a, const double *rdiag, double *r) {
+    const int tid = threadIdx.x % G;
+    for (int j = tid; j < n; j += G) {
+        int l = j;
+        for (int i = 0; i < j; ++i) { r[l] = a[i + (size_t)j * n]; l += n - 1 - i; }
+        r[l] = rdiag[j];
+    }
+    gsync<G>();
+}
+
+// qform: accumulate Q (n x n) in place from the Householder vectors; wa is scratch [n]
+template <int G>
+__device__ void qform_g(int n, double *q, double *wa) {
+    const int tid = threadIdx.x % G;
+    for (int j = 1 + tid; j < n; j += G)
+        for (int i = 0; i < j; ++i) q[i + (size_t)j * n] = 0.;
+    gsync<G>();
+    for (int l = 0; l < n; ++l) {
+        const int k = n - 1 - l;
+        double *ck = q + (size_t)k * n;
+        for (int i = k + tid; i < n; i += G) { wa[i] = ck[i]; ck[i] = (i == k) ? 1. : 0.; }
+        gsync<G>();
+        const double wk = wa[k];
+        if (wk != 0.) {
+            for (int j = k + tid; j < n; j += G) {
+                double *cj = q + (size_t)j * n;
+                double sum = 0.;
+                for (int i = k; i < n; ++i) sum += cj[i] * wa[i];
+                const double temp = sum / wk;
+                for (int i = k; i < n; ++i) cj[i] -= temp * wa[i];
+            }
+        }
+        gsync<G>();
+    }
+}
+
+// dogleg: x <- step; wa1, wa2 scratch
+template <int G>
+__device__ void dogleg_g(int n, const double *r, const double *diag, const double *qtb, double delta,
+                         double *x, double *wa1, double *wa2, double *red) {
+    const int tid = threadIdx.x % G;
+    gsync<G>();
+    // Gauss-Newton direction: back substitution, row by row from the bottom
+    for (int k = 1; k <= n; ++k) {
+        const int j = n - k;
+        const int jj = j * n - (j * (j - 1)) / 2;            // index of r(j,j)
+        double part = 0.;
+        for (int i = j + 1 + tid; i < n; i += G) part += r[jj + (i - j)] * x[i];
+        const double sum = gsum<G>(part, red);
+        double temp = r[jj];
+        if (temp == 0.) {
+            int l = j;
+            for (int i = 0; i <= j; ++i) { temp = fmax(temp, fabs(r[l])); l += n - 1 - i; }
+            temp = EPSMCH * temp;
+            if (temp == 0.) temp = EPSMCH;
+        }
+        if (tid == 0) x[j] = (qtb[j] - sum) / temp;
+        gsync<G>();
+    }
+    for (int j = tid; j < n; j += G) { wa1[j] = 0.; wa2[j] = diag[j] * x[j]; }
+    gsync<G>();
+    const double qnorm = enorm_g<G>(n, wa2, red);
+    if (qnorm <= delta) { gsync<G>(); return; }
+    // scaled gradient direction: wa1 = (R^T qtb) / diag
+    for (int i = tid; i < n; i += G) {
+        double s = 0.;
+        for (int j = 0; j <= i; ++j) s += r[j * n - (j * (j - 1)) / 2 + (i - j)] * qtb[j];
+        wa1[i] = s / diag[i];
+    }
+    gsync<G>();
+    const double gnorm = enorm_g<G>(n, wa1, red);
+    double sgnorm = 0., alpha = delta / qnorm;
+    if (gnorm != 0.) {
+        gsync<G>();
+        for (int j = tid; j < n; j += G) wa1[j] = (wa1[j] / gnorm) / diag[j];
+        gsync<G>();
+        for (int j = tid; j < n; j += G) {
+            const int jj = j * n - (j * (j - 1)) / 2;
+            double s = 0.;
+            for (int i = j; i < n; ++i) s += r[jj + (i - j)] * wa1[i];
+            wa2[j] = s;
+        }
+        gsync<G>();
+        double temp = enorm_g<G>(n, wa2, red);
+        sgnorm = (gnorm / temp) / temp;
+        alpha = 0.;
+        if (sgnorm < delta) {
+            const double bnorm = enorm_g<G>(n, qtb, red);
+            temp = (bnorm / gnorm) * (bnorm / qnorm) * (sgnorm / delta);
+            const double dq = delta / qnorm, sd = sgnorm / delta;
+            temp = temp - dq * (sd * sd) + sqrt((temp - dq) * (temp - dq) + (1. - dq * dq) * (1. - sd * sd));
+            alpha = (dq * (1. - sd * sd)) / temp;
+        }
+    }
+    const double temp = (1. - alpha) * fmin(sgnorm, delta);
+    gsync<G>();
+    for (int j = tid; j < n; j += G) x[j] = temp * wa1[j] + alpha * x[j];
+    gsync<G>();
+}
+
+// r1updt on the packed upper-triangular factor (m == n): (R + u v^T) -> R' with the 2(n-1) Givens
+// rotations recorded in v and w for r1mpyq.  cs/sn are scratch [n] each.
+template <int G>
+__device__ void r1updt_g(int n, double *s, const double *u, double *v, double *w, double *cs, double *sn) {
+    const int tid = threadIdx.x % G;
+    const double giant = DBL_MAX;
+    auto rowstart = [n](int j) { return j * n - (j * (j - 1)) / 2; };
+    gsync<G>();
+    // first sweep: the rotation coefficients depend on v only (scalar recurrence on v[n-1])
+    if (tid == 0) {
+        double vn = v[n - 1];
+        for (int j = n - 2; j >= 0; --j) {
+            double c = 1., sgl = 0.;
+            if (v[j] != 0.) {
+                double tau;
+                if (fabs(vn) < fabs(v[j])) {
+                    const double cotan = vn / v[j];
+                    sgl = .5 / sqrt(.25 + .25 * (cotan * cotan));
+                    c = sgl * cotan;
+                    tau = 1.;
+                    if (fabs(c) * giant > 1.) tau = 1. / c;
+                } else {
+                    const double tn = v[j] / vn;
+                    c = .5 / sqrt(.25 + .25 * (tn * tn));
+                    sgl = c * tn;
+                    tau = sgl;
+                }
+                vn = sgl * v[j] + c * vn;
+                v[j] = tau;
+                cs[j] = c; sn[j] = sgl;
+            } else {
+                cs[j] = 2.;            // marker: no rotation
+            }
+        }
+        v[n - 1] = vn;
+    }
+    gsync<G>();
+    // apply to the columns: column i is touched by rotations j = min(i, n-2) .. 0
+    for (int i = tid; i < n; i += G) {
+        double wi = (i == n - 1) ? s[rowstart(n - 1)] : 0.;
+        for (int j = (i < n - 1 ? i : n - 2); j >= 0; --j) {
+            if (cs[j] > 1.5) continue;
+            const int l = rowstart(j) + (i - j);
+            const double sl = s[l];
+            const double temp = cs[j] * sl - sn[j] * wi;
+            wi = sn[j] * sl + cs[j] * wi;
+            s[l] = temp;
+        }
+        w[i] = wi + v[n - 1] * u[i];                 // add the spike from the rank-1 update
+    }
+    gsync<G>();
+    // second sweep: eliminate the spike; rotation j depends on w[j] after rotations 0..j-1
+    for (int j = 0; j < n - 1; ++j) {
+        const int jj = rowstart(j);
+        const double wj = w[j], sjj = s[jj];
+        gsync<G>();
+        if (wj != 0.) {
+            double c, sgl, tau;
+            if (fabs(sjj) < fabs(wj)) {
+                const double cotan = sjj / wj;
+                sgl = .5 / sqrt(.25 + .25 * (cotan * cotan));
+                c = sgl * cotan;
+                tau = 1.;
+                if (fabs(c) * giant > 1.) tau = 1. / c;
+            } else {
+                const double tn = wj / sjj;
+                c = .5 / sqrt(.25 + .25 * (tn * tn));
+                sgl = c * tn;
+                tau = sgl;
+            }
+            for (int i = j + tid; i < n; i += G) {
+                const int l = jj + (i - j);
+                const double sl = s[l], wi = w[i];
+                s[l] = c * sl + sgl * wi;
+                w[i] = (i == j) ? tau : (-sgl * sl + c * wi);
+            }
+        }
+        gsync<G>();
+    }
+    if (tid == 0) s[rowstart(n - 1)] = w[n - 1];
+    gsync<G>();
+}
+
+// Rotation coefficients as r1mpyq reconstructs them from the stored tau values: scr = [c1 s1 c2 s2][n]
+template <int G>
+__device__ void r1coef_g(int n, const double *v, const double *w, double *scr) {
+    const int tid = threadIdx.x % G;
+    gsync<G>();
+    for (int j = tid; j < n - 1; j += G) {
+        double c, s;
+        if (fabs(v[j]) > 1.) { c = 1. / v[j]; s = sqrt(1. - c * c); }
+        else { s = v[j]; c = sqrt(1. - s * s); }
+        scr[j] = c; scr[n + j] = s;
+        if (fabs(w[j]) > 1.) { c = 1. / w[j]; s = sqrt(1. - c * c); }
+        else { s = w[j]; c = sqrt(1. - s * s); }
+        scr[2 * n + j] = c; scr[3 * n + j] = s;
+    }
+    gsync<G>();
+}
+
+// r1mpyq: apply the recorded rotations to A (m x n, column-major, lda) -- one thread per row
+template <int G>
+__device__ void r1mpyq_g(int m, int n, double *a, int lda, const double *scr) {
+    const int tid = threadIdx.x % G;
+    const double *c1 = scr, *s1 = scr + n, *c2 = scr + 2 * n, *s2 = scr + 3 * n;
+    gsync<G>();
+    for (int i = tid; i < m; i += G) {
+        double an = a[i + (size_t)(n - 1) * lda];
+        for (int j = n - 2; j >= 0; --j) {
+            const double aj = a[i + (size_t)j * lda];
+            a[i + (size_t)j * lda] = c1[j] * aj - s1[j] * an;
+            an = s1[j] * aj + c1[j] * an;
+        }
+        for (int j = 0; j < n - 1; ++j) {
+            const double aj = a[i + (size_t)j * lda];
+            a[i + (size_t)j * lda] = c2[j] * aj + s2[j] * an;
+            an = -s2[j] * aj + c2[j] * an;
+        }
+        a[i + (size_t)(n - 1) * lda] = an;
+    }
+    gsync<G>();
+}
+
+// ---- kernel 2: advance every problem that received its function values -------------------------
+template <int MODEL, int G>
+__global__ void __launch_bounds__((G == 32) ? 128 : G)
+advance(SolverDev D, int cur) {
+    constexpr int GROUPS = (G == 32) ? 4 : 1;
+    __shared__ double red_all[GROUPS][8];
+    const int grp = (G == 32) ? (threadIdx.x >> 5) : 0;
+    const int tid = threadIdx.x % G;
+    double *red = red_all[grp];
+    const int nres = D.counts[cur * 2 + 0], njac = D.counts[cur * 2 + 1];
+    const int *res_list = D.lists + (size_t)(cur * 2 + 0) * D.B;
+    const int *jac_list = D.lists + (size_t)(cur * 2 + 1) * D.B;
+    int *next_res = D.lists + (size_t)((1 - cur) * 2 + 0) * D.B;
+    int *next_jac = D.lists + (size_t)((1 - cur) * 2 + 1) * D.B;
+    int *next_cnt = D.counts + (1 - cur) * 2;
+    const int n = D.P;
+    const double p1 = .1, p5 = .5, p001 = .001, p0001 = 1e-4;
+
+    for (long g = (long)blockIdx.x * GROUPS + grp; g < (long)nres + njac; g += (long)gridDim.x * GROUPS) {
+        const long b = (g < nres) ? res_list[g] : jac_list[g - nres];
+        int *is = D.istate + b * I_COUNT;
+        double *ds = D.dstate + b * D_COUNT;
+        double *x = D.x + b * n, *xe = D.xe + b * n, *fvec = D.fvec + b * n, *diag = D.diag + b * n;
+        double *qtf = D.qtf + b * n, *wa1 = D.wa1 + b * n, *wa2 = D.wa2 + b * n, *wa3 = D.wa3 + b * n, *wa4 = D.wa4 + b * n;
+        double *fjac = D.fjac + (size_t)b * n * n, *r = D.r + (size_t)b * D.LR, *scr = D.scr + (size_t)b * 4 * n;
+        const double *jends_b = D.jends + (size_t)b * D.nJ * D.REC;
+        gsync<G>();
+        int phase = is[I_PHASE];
+        bool need_dogleg = false;
+
+        if (phase == PH_F0) {
+            // first residual: fvec = F(x)
+            const int trial = 1 - is[I_BASE];
+            const double *te = D.ends + ((b * 2 + trial) * D.M) * D.REC;
+            if (tid == 0) assemble<MODEL>(D, b, -1, 0.0, te, jends_b, [&](int i, double v) { fvec[i] = v; });
+            gsync<G>();
+            const double fnorm = enorm_g<G>(n, fvec, red);
+            gsync<G>();
+            if (tid == 0) {
+                is[I_BASE] = trial;
+                is[I_NFEV] = 1;
+                ds[D_FNORM] = fnorm;
+                is[I_ITER] = 1; is[I_NCSUC] = 0; is[I_NCFAIL] = 0; is[I_NSLOW1] = 0; is[I_NSLOW2] = 0;
+            }
+            if (D.run_mode == RUN_RESIDUAL) {
+                if (tid == 0) is[I_PHASE] = PH_IDLE;
+            } else {
+                if (tid == 0) {
+                    is[I_PHASE] = PH_JAC;
+                    next_jac[atomicAdd(&next_cnt[1], 1)] = (int)b;
+                }
+            }
+        } else if (phase == PH_JAC) {
+            // forward-difference Jacobian from the perturbed segments (fdjac1, dense)
+            const double *be = D.ends + ((b * 2 + is[I_BASE]) * D.M) * D.REC;
+            for (int j = tid; j < n; j += G) {
+                const double h = fd_step(xe[j], D.epsfcn);
+                double *colj = fjac + (size_t)j * n;
+                assemble<MODEL>(D, b, j, h, be, jends_b, [&](int i, double v) { colj[i] = (v - fvec[i]) / h; });
+            }
+            gsync<G>();
+            if (D.run_mode == RUN_FDJAC) {
+                if (tid == 0) is[I_PHASE] = PH_IDLE;
+            } else {
+                if (tid == 0) { is[I_NFEV] += n; is[I_JEVAL] = 1; }
+                for (int i = tid; i < n; i += G) qtf[i] = fvec[i];
+                // wa1 = rdiag, wa2 = acnorm
+                qrfac_g<G>(n, fjac, wa1, wa2, qtf, red);
+                const int iter = is[I_ITER];
+                if (iter == 1) {
+                    for (int j = tid; j < n; j += G) {
+                        double dj = wa2[j];
+                        if (dj == 0.) dj = 1.;
+                        diag[j] = dj;
+                        wa3[j] = dj * x[j];
+                    }
+                    gsync<G>();
+                    const double xnorm = enorm_g<G>(n, wa3, red);
+                    double delta = D.factor * xnorm;
+                    if (delta == 0.) delta = D.factor;
+                    gsync<G>();
+                    if (tid == 0) { ds[D_XNORM] = xnorm; ds[D_DELTA] = delta; }
+                }
+                pack_r_g<G>(n, fjac, wa1, r);
+                qform_g<G>(n, fjac, wa1);
+                for (int j = tid; j < n; j += G) diag[j] = fmax(diag[j], wa2[j]);
+                gsync<G>();
+                need_dogleg = true;
+            }
+        } else if (phase == PH_TRIAL) {
+            // wa4 = F(x + p)
+            const int trial = 1 - is[I_BASE];
+            const double *te = D.ends + ((b * 2 + trial) * D.M) * D.REC;
+            if (tid == 0) assemble<MODEL>(D, b, -1, 0.0, te, jends_b, [&](int i, double v) { wa4[i] = v; });
+            gsync<G>();
+            const double fnorm1 = enorm_g<G>(n, wa4, red);
+            double fnorm = ds[D_FNORM], delta = ds[D_DELTA], xnorm = ds[D_XNORM];
+            const double pnorm = ds[D_PNORM];
+            int iter = is[I_ITER], ncsuc = is[I_NCSUC], ncfail = is[I_NCFAIL], nslow1 = is[I_NSLOW1], nslow2 = is[I_NSLOW2];
+            const int jeval = is[I_JEVAL];
+            const int nfev = is[I_NFEV] + 1;
+            double actred = -1.;
+            if (fnorm1 < fnorm) { const double q = fnorm1 / fnorm; actred = 1. - q * q; }
+            // predicted reduction: wa3 = qtf + R * wa1
+            gsync<G>();
+            for (int i = tid; i < n; i += G) {
+                const int jj = i * n - (i * (i - 1)) / 2;
+                double sum = 0.;
+                for (int j = i; j < n; ++j) sum += r[jj + (j - i)] * wa1[j];
+                wa3[i] = qtf[i] + sum;
+            }
+            gsync<G>();
+            const double temp = enorm_g<G>(n, wa3, red);
+            double prered = 0.;
+            if (temp < fnorm) { const double q = temp / fnorm; prered = 1. - q * q; }
+            double ratio = 0.;
+            if (prered > 0.) ratio = actred / prered;
+            if (ratio < p1) {
+                ncsuc = 0; ++ncfail; delta = p5 * delta;
+            } else {
+                ncfail = 0; ++ncsuc;
+                if (ratio >= p5 || ncsuc > 1) delta = fmax(delta, pnorm / p5);
+                if (fabs(ratio - 1.) <= p1) delta = pnorm / p5;
+            }
+            int base = is[I_BASE];
+            gsync<G>();
+            if (ratio >= p0001) {
+                // successful iteration: x <- x + p, fvec <- wa4
+                for (int j = tid; j < n; j += G) {
+                    const double xj = xe[j];
+                    x[j] = xj;
+                    wa2[j] = diag[j] * xj;
+                    fvec[j] = wa4[j];
+                }
+                gsync<G>();
+                xnorm = enorm_g<G>(n, wa2, red);
+                fnorm = fnorm1;
+                ++iter;
+                base = trial;
+            }
+            ++nslow1;
+            if (actred >= p001) nslow1 = 0;
+            if (jeval) ++nslow2;
+            if (actred >= p1) nslow2 = 0;
+            int info = 0;
+            if (delta <= D.xtol * xnorm || fnorm == 0.) info = 1;
+            if (info == 0) {
+                if (nfev >= D.maxfev) info = 2;
+                if (p1 * fmax(p1 * delta, pnorm) <= EPSMCH * xnorm) info = 3;
+                if (nslow2 == 5) info = 4;
+                if (nslow1 == 10) info = 5;
+            }
+            gsync<G>();
+            if (tid == 0) {
+                is[I_ITER] = iter; is[I_NCSUC] = ncsuc; is[I_NCFAIL] = ncfail; is[I_NSLOW1] = nslow1; is[I_NSLOW2] = nslow2;
+                is[I_NFEV] = nfev; is[I_BASE] = base;
+                ds[D_FNORM] = fnorm; ds[D_DELTA] = delta; ds[D_XNORM] = xnorm;
+            }
+            if (info != 0) {
+                if (tid == 0) { is[I_INFO] = info; is[I_PHASE] = PH_IDLE; }      // retire
+            } else if (ncfail == 2) {
+                // re-evaluate the Jacobian at x
+                for (int j = tid; j < n; j += G) xe[j] = x[j];
+                if (tid == 0) {
+                    is[I_PHASE] = PH_JAC;
+                    next_jac[atomicAdd(&next_cnt[1], 1)] = (int)b;
+                }
+            } else {
+                // rank-one (Broyden) update of the QR factors
+                for (int j = tid; j < n; j += G) {
+                    const double *cj = fjac + (size_t)j * n;
+                    double sum = 0.;
+                    for (int i = 0; i < n; ++i) sum += cj[i] * wa4[i];
+                    wa2[j] = (sum - wa3[j]) / pnorm;
+                    wa1[j] = diag[j] * ((diag[j] * wa1[j]) / pnorm);
+                    if (ratio >= p0001) qtf[j] = sum;
+                }
+                r1updt_g<G>(n, r, wa1, wa2, wa3, scr, scr + n);
+                r1coef_g<G>(n, wa2, wa3, scr);
+                r1mpyq_g<G>(n, n, fjac, n, scr);
+                r1mpyq_g<G>(1, n, qtf, 1, scr);
+                if (tid == 0) is[I_JEVAL] = 0;
+                need_dogleg = true;
+            }
+        }
+
+        if (need_dogleg) {
+            const double delta = ds[D_DELTA];
+            dogleg_g<G>(n, r, diag, qtf, delta, wa1, wa2, wa3, red);
+            for (int j = tid; j < n; j += G) {
+                const double pj = -wa1[j];
+                wa1[j] = pj;
+                xe[j] = x[j] + pj;            // trial point (MINPACK's wa2)
+                wa3[j] = diag[j] * pj;
+            }
+            gsync<G>();
+            const double pnorm = enorm_g<G>(n, wa3, red);
+            gsync<G>();
+            if (tid == 0) {
+                ds[D_PNORM] = pnorm;
+                if (is[I_ITER] == 1) ds[D_DELTA] = fmin(delta, pnorm);
+                is[I_PHASE] = PH_TRIAL;
+                next_res[atomicAdd(&next_cnt[0], 1)] = (int)b;
+            }
+        }
+        gsync<G>();
+    }
+}
+
+// ---- small kernels -------------------------------------------------------------------------------
+__global__ void solver_init(SolverDev D, const double *x_in, long first) {
+    // problems [first, first + B): copy the unknowns, reset the state, enqueue the first residual
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < D.B * D.P) {
+        const double v = x_in[first * D.P + i];
+        D.x[i] = v;
+        D.xe[i] = v;
+    }
+    if (i < D.B) {
+        int *is = D.istate + i * I_COUNT;
+        for (int k = 0; k < I_COUNT; ++k) is[k] = 0;
+        is[I_PHASE] = PH_F0;
+        D.lists[i] = (int)i;          // lists[0][0] = residual requests of round 0
+        for (int k = 0; k < D_COUNT; ++k) D.dstate[i * D_COUNT + k] = 0.;
+    }
+    if (i == 0) {
+        D.counts[0] = (int)D.B; D.counts[1] = 0; D.counts[2] = 0; D.counts[3] = 0;
+    }
+}
+
+__global__ void solver_finish(SolverDev D, long first, double *x_out, double *fvec_out, double *fjac_out,
+                              int *info, int *nfev, double *fnorm) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (x_out && i < D.B * D.P) x_out[first * D.P + i] = D.x[i];
+    if (fvec_out && i < D.B * D.P) fvec_out[first * D.P + i] = D.fvec[i];
+    if (fjac_out && i < D.B * (long)D.P * D.P) fjac_out[first * (long)D.P * D.P + i] = D.fjac[i];
+    if (i < D.B) {
+        const int *is = D.istate + i * I_COUNT;
+        // a problem still in flight when the round limit is hit reports info 2-like "not finished"
+        if (info) info[first + i] = (is[I_PHASE] == PH_IDLE) ? is[I_INFO] : 2;
+        if (nfev) nfev[first + i] = is[I_NFEV];
+        if (fnorm) fnorm[first + i] = D.dstate[i * D_COUNT + D_FNORM];
+    }
+}
+
+// ---- host-side workspace ---------------------------------------------------------------------------
+struct SolverWorkspace {
+    void *blob = nullptr;
+    size_t cap = 0;
+    int *h_counts = nullptr;          // pinned
+    cudaEvent_t ev = nullptr;
+    void release() {
+        if (blob) cudaFree(blob);
+        blob = nullptr; cap = 0;
+        if (h_counts) cudaFreeHost(h_counts);
+        h_counts = nullptr;
+        if (ev) cudaEventDestroy(ev);
+        ev = nullptr;
+    }
+    double bytes() const { return (double)cap; }
+};
+
+}  // namespace socp

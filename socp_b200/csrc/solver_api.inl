@@ -1,8 +1,405 @@
-// placeholder
-extern "C" {
-int socp_residual_batch(socp_ctx *ctx, const socp_shape *, long, const double *, const double *, const double *, const double *, double *, int) { return fail(ctx, SOCP_ERR_UNSUPPORTED, "not built yet"); }
-int socp_fdjac_batch(socp_ctx *ctx, const socp_shape *, long, const double *, const double *, const double *, const double *, double, double *, int) { return fail(ctx, SOCP_ERR_UNSUPPORTED, "not built yet"); }
-int socp_solve_batch(socp_ctx *ctx, const socp_shape *, long, const double *, const double *, const double *, double *, double, int, int *, int *, double *, int) { return fail(ctx, SOCP_ERR_UNSUPPORTED, "not built yet"); }
-int socp_continuation_param_batch(socp_ctx *ctx, const socp_shape *, long, double *, const double *, const double *, double *, double, int, double, int, const double *, double, int *, int *) { return fail(ctx, SOCP_ERR_UNSUPPORTED, "not built yet"); }
-int socp_continuation_boundary_batch(socp_ctx *ctx, const socp_shape *, long, const double *, const double *, const double *, const double *, const double *, double *, double, int, double, double, int *, int *) { return fail(ctx, SOCP_ERR_UNSUPPORTED, "not built yet"); }
+// socp_b200/csrc/solver_api.inl -- host side of the batched residual / Jacobian / solve entry
+// points (included at the end of api.cu).  Host glue only: shapes, work-item tables, workspace
+// carving, the round loop and the continuation state machines; no arithmetic of the hot path.
+
+namespace {
+
+struct Carver {
+    char *base;
+    size_t off = 0;
+    explicit Carver(void *b) : base((char *)b) {}
+    template <typename T> T *take(size_t count) {
+        off = (off + 255) & ~(size_t)255;
+        T *p = base ? (T *)(base + off) : nullptr;
+        off += count * sizeof(T);
+        return p;
+    }
+};
+
+struct HostPlan {
+    SolverDev D;
+    std::vector<int> jac_col, jac_seg, col_item0, col_nseg;
+    size_t bytes_per_problem = 0;
+    size_t table_ints = 0;
+};
+
+int make_plan(socp_ctx *ctx, const socp_shape *shape, HostPlan &pl) {
+    if (!shape) return fail(ctx, SOCP_ERR_ARG, "shape is NULL");
+    const int P = socp_num_param(shape);
+    if (P < 0) return fail(ctx, SOCP_ERR_ARG, "bad shape (model id / numMulti)");
+    SolverDev &D = pl.D;
+    memset(&D, 0, sizeof D);
+    D.model_id = shape->model_id;
+    D.dim = kDim[D.model_id];
+    D.N = 2 * D.dim;
+    D.M = shape->num_multi;
+    D.S = shape->step_nbr > 0 ? shape->step_nbr : kSteps[D.model_id];
+    D.P = P;
+    D.np = kNP[D.model_id];
+    D.REC = D.N + 2;
+    D.LR = P * (P + 1) / 2;
+    D.nfree = P - D.N * D.M;
+    for (int j = 0; j <= D.M; ++j) {
+        const int mt = shape->mode_t[j];
+        if (mt < SOCP_FIXED || mt > SOCP_CONTINUOUS) return fail(ctx, SOCP_ERR_ARG, "bad mode_t");
+        D.mode_t[j] = mt;
+        for (int k = 0; k < D.dim; ++k) D.mode_X[j][k] = shape->mode_X[j][k];
+    }
+    if (D.mode_t[0] == SOCP_CONTINUOUS || D.mode_t[D.M] == SOCP_CONTINUOUS)
+        return fail(ctx, SOCP_ERR_ARG, "the first and last node times must be FIXED or FREE");
+    // Jacobian work items: a state/costate unknown of node i only moves segment i; a free time
+    // moves the whole time line, so every segment is re-integrated for it.
+    pl.col_item0.assign(P, 0);
+    pl.col_nseg.assign(P, 1);
+    for (int j = 0; j < P; ++j) {
+        pl.col_item0[j] = (int)pl.jac_col.size();
+        if (j < D.N * D.M) {
+            pl.jac_col.push_back(j);
+            pl.jac_seg.push_back(j / D.N);
+        } else {
+            pl.col_nseg[j] = D.M;
+            for (int s = 0; s < D.M; ++s) { pl.jac_col.push_back(j); pl.jac_seg.push_back(s); }
+        }
+    }
+    D.nJ = (int)pl.jac_col.size();
+    pl.table_ints = 2 * (size_t)D.nJ + 2 * (size_t)P;
+    // persistent bytes per problem
+    size_t dbl = (size_t)P * 10 + 4 * (size_t)P + (size_t)P * P + D.LR + (size_t)(2 * D.M + D.nJ) * D.REC + D_COUNT;
+    pl.bytes_per_problem = dbl * sizeof(double) + (I_COUNT + 4) * sizeof(int) + 2048 / 64;
+    return SOCP_OK;
 }
+
+// carve the solver workspace for a wave of Bw problems; returns the total size
+size_t carve(HostPlan &pl, void *blob, long Bw) {
+    SolverDev &D = pl.D;
+    Carver c(blob);
+    const size_t P = D.P;
+    int *tab = c.take<int>(pl.table_ints);
+    D.jac_col = tab;
+    D.jac_seg = tab ? tab + D.nJ : nullptr;
+    D.col_item0 = tab ? tab + 2 * D.nJ : nullptr;
+    D.col_nseg = tab ? tab + 2 * D.nJ + P : nullptr;
+    D.x = c.take<double>(Bw * P); D.xe = c.take<double>(Bw * P); D.fvec = c.take<double>(Bw * P);
+    D.diag = c.take<double>(Bw * P); D.qtf = c.take<double>(Bw * P);
+    D.wa1 = c.take<double>(Bw * P); D.wa2 = c.take<double>(Bw * P); D.wa3 = c.take<double>(Bw * P);
+    D.wa4 = c.take<double>(Bw * P); D.scr = c.take<double>(Bw * 4 * P);
+    D.fjac = c.take<double>(Bw * P * P);
+    D.r = c.take<double>(Bw * (size_t)D.LR);
+    D.ends = c.take<double>(Bw * 2 * (size_t)D.M * D.REC);
+    D.jends = c.take<double>(Bw * (size_t)D.nJ * D.REC);
+    D.dstate = c.take<double>(Bw * D_COUNT);
+    D.istate = c.take<int>(Bw * I_COUNT);
+    D.lists = c.take<int>(4 * (size_t)Bw);
+    D.counts = c.take<int>(8);
+    return c.off + 256;
+}
+
+template <int MODEL>
+void launch_round(socp_ctx *ctx, const SolverDev &D, int cur, int grid_int, int grid_adv) {
+    integrate_worklist<MODEL><<<grid_int, 128, 0, ctx->stream>>>(D, cur);
+    if (D.P <= 32) advance<MODEL, 32><<<grid_adv, 128, 0, ctx->stream>>>(D, cur);
+    else advance<MODEL, 128><<<grid_adv, 128, 0, ctx->stream>>>(D, cur);
+    ctx->launches += 2;
+    ctx->rounds += 1;
+}
+
+void launch_round_any(socp_ctx *ctx, const SolverDev &D, int cur, int gi, int ga) {
+    switch (D.model_id) {
+    case SOCP_GODDARD: launch_round<GODDARD>(ctx, D, cur, gi, ga); break;
+    case SOCP_DOUBLE_INTEGRATOR: launch_round<DOUBLE_INTEGRATOR>(ctx, D, cur, gi, ga); break;
+    case SOCP_COVID19: launch_round<COVID19>(ctx, D, cur, gi, ga); break;
+    case SOCP_VTOL_UAV: launch_round<VTOL_UAV>(ctx, D, cur, gi, ga); break;
+    case SOCP_INTERCEPTOR: launch_round<INTERCEPTOR>(ctx, D, cur, gi, ga); break;
+    }
+}
+
+// Run the state machine for B problems given DEVICE pointers; waves sized to the free memory.
+int run_solver(socp_ctx *ctx, const socp_shape *shape, long B, const double *d_mparams, const double *d_time,
+               const double *d_Xb, const double *d_x_in, int run_mode, double xtol, int maxfev, double epsfcn,
+               double *d_x_out, double *d_fvec_out, double *d_fjac_out, int *d_info, int *d_nfev, double *d_fnorm) {
+    HostPlan pl;
+    int rc = make_plan(ctx, shape, pl);
+    if (rc != SOCP_OK) return rc;
+    if (B == 0) return SOCP_OK;
+    SolverDev &D = pl.D;
+    // wave size from the memory that is free now plus what the workspace already holds
+    size_t free_b = 0, total_b = 0;
+    CUDA_TRY(ctx, cudaMemGetInfo(&free_b, &total_b));
+    const size_t budget = (size_t)((free_b + ctx->solver.cap) * 0.85);
+    long wave = (long)std::min<size_t>((size_t)B, std::max<size_t>(1, (budget - (1 << 20)) / pl.bytes_per_problem));
+    if (wave < 1) return fail(ctx, SOCP_ERR_NOMEM, "not enough device memory for one problem");
+    size_t need = carve(pl, nullptr, wave);
+    if (need > ctx->solver.cap) {
+        if (ctx->solver.blob) cudaFree(ctx->solver.blob);
+        ctx->solver.blob = nullptr;
+        ctx->solver.cap = 0;
+        if (cudaMalloc(&ctx->solver.blob, need) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(ctx, SOCP_ERR_NOMEM, "cudaMalloc failed for the solver workspace (" + std::to_string(need) + " bytes)");
+        }
+        ctx->solver.cap = need;
+    }
+    if (!ctx->solver.h_counts) {
+        CUDA_TRY(ctx, cudaHostAlloc((void **)&ctx->solver.h_counts, 8 * sizeof(int), cudaHostAllocDefault));
+        CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->solver.ev, cudaEventDisableTiming));
+    }
+    carve(pl, ctx->solver.blob, wave);
+    // work-item tables
+    {
+        std::vector<int> tab;
+        tab.insert(tab.end(), pl.jac_col.begin(), pl.jac_col.end());
+        tab.insert(tab.end(), pl.jac_seg.begin(), pl.jac_seg.end());
+        tab.insert(tab.end(), pl.col_item0.begin(), pl.col_item0.end());
+        tab.insert(tab.end(), pl.col_nseg.begin(), pl.col_nseg.end());
+        CUDA_TRY(ctx, cudaMemcpyAsync((void *)D.jac_col, tab.data(), tab.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));      // tab is a stack-lifetime vector
+    }
+    D.xtol = xtol; D.epsfcn = epsfcn; D.factor = 1.0; D.maxfev = maxfev; D.run_mode = run_mode;
+    D.counters = ctx->d_counters;
+    const int grid_int = ctx->sm_count * 8;
+    const int grid_adv = ctx->sm_count * 8;
+    const int check_every = (run_mode == RUN_SOLVE) ? 8 : 1;
+    const long max_rounds = (run_mode == RUN_SOLVE) ? (long)maxfev + 8 : (run_mode == RUN_FDJAC ? 2 : 1);
+
+    for (long first = 0; first < B; first += wave) {
+        const long Bw = std::min(wave, B - first);
+        D.B = Bw;
+        D.mparams = d_mparams + first * D.np;
+        D.time = d_time + first * (D.M + 1);
+        D.Xb = d_Xb + first * (D.M + 1) * D.dim;
+        const long nthreads = Bw * D.P;
+        solver_init<<<(unsigned)((nthreads + 255) / 256), 256, 0, ctx->stream>>>(D, d_x_in, first);
+        ctx->launches += 1;
+        int cur = 0;
+        for (long round = 0; round < max_rounds; ++round) {
+            launch_round_any(ctx, D, cur, grid_int, grid_adv);
+            cur = 1 - cur;
+            if (run_mode == RUN_SOLVE && (round % check_every) == check_every - 1) {
+                CUDA_TRY(ctx, cudaMemcpyAsync(ctx->solver.h_counts, D.counts, 4 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+                CUDA_TRY(ctx, cudaEventRecord(ctx->solver.ev, ctx->stream));
+                CUDA_TRY(ctx, cudaEventSynchronize(ctx->solver.ev));
+                if (ctx->solver.h_counts[cur * 2] + ctx->solver.h_counts[cur * 2 + 1] == 0) break;
+            }
+        }
+        const long nfin = std::max<long>(nthreads, d_fjac_out ? Bw * (long)D.P * D.P : 0);
+        solver_finish<<<(unsigned)((nfin + 255) / 256), 256, 0, ctx->stream>>>(D, first, d_x_out, d_fvec_out, d_fjac_out, d_info, d_nfev, d_fnorm);
+        ctx->launches += 1;
+        CUDA_TRY(ctx, cudaGetLastError());
+    }
+    return SOCP_OK;
+}
+
+int check_problem_args(socp_ctx *ctx, const socp_shape *shape, long B, const void *a, const void *b, const void *c,
+                       const void *d, const void *e) {
+    if (!ctx) return SOCP_ERR_ARG;
+    if (!shape || B < 0 || !a || !b || !c || !d || !e) return fail(ctx, SOCP_ERR_ARG, "NULL argument or negative batch size");
+    if (socp_num_param(shape) < 0) return fail(ctx, SOCP_ERR_ARG, "bad shape");
+    return SOCP_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int socp_residual_batch(socp_ctx *ctx, const socp_shape *shape, long B, const double *mparams,
+                        const double *time, const double *Xb, const double *x, double *fvec, int mem) {
+    int rc = check_problem_args(ctx, shape, B, mparams, time, Xb, x, fvec);
+    if (rc != SOCP_OK || B == 0) return rc;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const int P = socp_num_param(shape), dim = kDim[shape->model_id], np = kNP[shape->model_id], M = shape->num_multi;
+    const double *d_mp = stage_in(ctx, SLOT_MPARAMS, mparams, (size_t)B * np, mem, &rc);
+    const double *d_time = stage_in(ctx, SLOT_TIME, time, (size_t)B * (M + 1), mem, &rc);
+    const double *d_Xb = stage_in(ctx, SLOT_XB, Xb, (size_t)B * (M + 1) * dim, mem, &rc);
+    const double *d_x = stage_in(ctx, SLOT_X, x, (size_t)B * P, mem, &rc);
+    double *d_f = stage_out(ctx, SLOT_FVEC, fvec, (size_t)B * P, mem, &rc);
+    if (rc != SOCP_OK) return rc;
+    rc = run_solver(ctx, shape, B, d_mp, d_time, d_Xb, d_x, RUN_RESIDUAL, 0., 1, 1e-15, nullptr, d_f, nullptr, nullptr, nullptr, nullptr);
+    if (rc != SOCP_OK) return rc;
+    if ((rc = fetch_out(ctx, fvec, d_f, (size_t)B * P, mem)) != SOCP_OK) return rc;
+    if (mem == SOCP_HOST) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return SOCP_OK;
+}
+
+int socp_fdjac_batch(socp_ctx *ctx, const socp_shape *shape, long B, const double *mparams,
+                     const double *time, const double *Xb, const double *x, double epsfcn,
+                     double *fjac, int mem) {
+    int rc = check_problem_args(ctx, shape, B, mparams, time, Xb, x, fjac);
+    if (rc != SOCP_OK || B == 0) return rc;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const int P = socp_num_param(shape), dim = kDim[shape->model_id], np = kNP[shape->model_id], M = shape->num_multi;
+    const double *d_mp = stage_in(ctx, SLOT_MPARAMS, mparams, (size_t)B * np, mem, &rc);
+    const double *d_time = stage_in(ctx, SLOT_TIME, time, (size_t)B * (M + 1), mem, &rc);
+    const double *d_Xb = stage_in(ctx, SLOT_XB, Xb, (size_t)B * (M + 1) * dim, mem, &rc);
+    const double *d_x = stage_in(ctx, SLOT_X, x, (size_t)B * P, mem, &rc);
+    double *d_j = stage_out(ctx, SLOT_FJAC, fjac, (size_t)B * P * P, mem, &rc);
+    if (rc != SOCP_OK) return rc;
+    rc = run_solver(ctx, shape, B, d_mp, d_time, d_Xb, d_x, RUN_FDJAC, 0., 1, epsfcn, nullptr, nullptr, d_j, nullptr, nullptr, nullptr);
+    if (rc != SOCP_OK) return rc;
+    if ((rc = fetch_out(ctx, fjac, d_j, (size_t)B * P * P, mem)) != SOCP_OK) return rc;
+    if (mem == SOCP_HOST) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return SOCP_OK;
+}
+
+int socp_solve_batch(socp_ctx *ctx, const socp_shape *shape, long B, const double *mparams,
+                     const double *time, const double *Xb, double *x, double xtol, int maxfev,
+                     int *info, int *nfev, double *fnorm, int mem) {
+    int rc = check_problem_args(ctx, shape, B, mparams, time, Xb, x, info);
+    if (rc != SOCP_OK) return rc;
+    if (xtol < 0. || maxfev <= 0) {
+        // hybrd's own argument check: info = 0 and x untouched (MINPACK hybrd, "check the input parameters")
+        if (mem == SOCP_HOST) for (long b = 0; b < B; ++b) { info[b] = 0; if (nfev) nfev[b] = 0; }
+        return fail(ctx, SOCP_ERR_ARG, "xtol < 0 or maxfev <= 0");
+    }
+    if (B == 0) return SOCP_OK;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const int P = socp_num_param(shape), dim = kDim[shape->model_id], np = kNP[shape->model_id], M = shape->num_multi;
+    const double *d_mp = stage_in(ctx, SLOT_MPARAMS, mparams, (size_t)B * np, mem, &rc);
+    const double *d_time = stage_in(ctx, SLOT_TIME, time, (size_t)B * (M + 1), mem, &rc);
+    const double *d_Xb = stage_in(ctx, SLOT_XB, Xb, (size_t)B * (M + 1) * dim, mem, &rc);
+    const double *d_xin = stage_in(ctx, SLOT_X, (const double *)x, (size_t)B * P, mem, &rc);
+    double *d_x = (mem == SOCP_DEVICE) ? x : (double *)d_xin;
+    int *d_info = stage_out(ctx, SLOT_INFO, info, (size_t)B, mem, &rc);
+    int *d_nfev = stage_out(ctx, SLOT_NFEV, nfev, (size_t)B, mem, &rc);
+    double *d_fn = stage_out(ctx, SLOT_FNORM, fnorm, (size_t)B, mem, &rc);
+    if (rc != SOCP_OK) return rc;
+    rc = run_solver(ctx, shape, B, d_mp, d_time, d_Xb, d_xin, RUN_SOLVE, xtol, maxfev, 1e-15, d_x, nullptr, nullptr, d_info, d_nfev, d_fn);
+    if (rc != SOCP_OK) return rc;
+    if ((rc = fetch_out(ctx, x, d_x, (size_t)B * P, mem)) != SOCP_OK) return rc;
+    if ((rc = fetch_out(ctx, info, d_info, (size_t)B, mem)) != SOCP_OK) return rc;
+    if ((rc = fetch_out(ctx, nfev, d_nfev, (size_t)B, mem)) != SOCP_OK) return rc;
+    if ((rc = fetch_out(ctx, fnorm, d_fn, (size_t)B, mem)) != SOCP_OK) return rc;
+    if (mem == SOCP_HOST) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return SOCP_OK;
+}
+
+// ---- continuation (host state machines around socp_solve_batch) ---------------------------------
+// Each problem runs the reference's homotopy loop (shooting.cpp:598-692 / :695-778) with its own
+// b, b_prec; all problems still in their loop are solved together, one batched solve per pass.
+
+int socp_continuation_param_batch(socp_ctx *ctx, const socp_shape *shape, long B, double *mparams,
+                                  const double *time, const double *Xb, double *x, double xtol,
+                                  int maxfev, double step, int param_idx, const double *goal,
+                                  double step_min, int *info, int *calls) {
+    int rc = check_problem_args(ctx, shape, B, mparams, time, Xb, x, info);
+    if (rc != SOCP_OK) return rc;
+    const int P = socp_num_param(shape), dim = kDim[shape->model_id], np = kNP[shape->model_id], M = shape->num_multi;
+    if (param_idx < 0 || param_idx >= np || !goal) return fail(ctx, SOCP_ERR_ARG, "bad parameter index / goal");
+    if (step <= 0) step = 1.0;                              // shooting.cpp:352-355
+    std::vector<double> Rstart(B), b(B), b_prec(B, 0.0), tmp((size_t)B * P);
+    std::vector<char> active(B, 1);
+    for (long k = 0; k < B; ++k) {
+        Rstart[k] = mparams[k * np + param_idx];
+        b[k] = std::min(step, 1.0);
+        mparams[k * np + param_idx] = (1 - b[k]) * Rstart[k] + b[k] * goal[k];
+        info[k] = 0;
+        if (calls) { calls[2 * k] = 0; calls[2 * k + 1] = 0; }
+    }
+    memcpy(tmp.data(), x, sizeof(double) * (size_t)B * P);
+    std::vector<long> idx;
+    std::vector<double> wx, wmp, wtime, wXb, wfn;
+    std::vector<int> winfo, wnfev;
+    for (;;) {
+        idx.clear();
+        for (long k = 0; k < B; ++k) if (active[k]) idx.push_back(k);
+        if (idx.empty()) break;
+        const long A = (long)idx.size();
+        wx.resize((size_t)A * P); wmp.resize((size_t)A * np); wtime.resize((size_t)A * (M + 1)); wXb.resize((size_t)A * (M + 1) * dim);
+        winfo.resize(A); wnfev.resize(A); wfn.resize(A);
+        for (long a = 0; a < A; ++a) {
+            const long k = idx[a];
+            memcpy(&wx[a * P], &tmp[k * P], sizeof(double) * P);
+            memcpy(&wmp[a * np], &mparams[k * np], sizeof(double) * np);
+            memcpy(&wtime[a * (M + 1)], &time[k * (M + 1)], sizeof(double) * (M + 1));
+            memcpy(&wXb[a * (M + 1) * dim], &Xb[k * (M + 1) * dim], sizeof(double) * (M + 1) * dim);
+        }
+        rc = socp_solve_batch(ctx, shape, A, wmp.data(), wtime.data(), wXb.data(), wx.data(), xtol, maxfev,
+                              winfo.data(), wnfev.data(), wfn.data(), SOCP_HOST);
+        if (rc != SOCP_OK) return rc;
+        for (long a = 0; a < A; ++a) {
+            const long k = idx[a];
+            const int ret = winfo[a];
+            info[k] = ret;
+            if (calls) { calls[2 * k] += 1; calls[2 * k + 1] += wnfev[a]; }
+            if (ret != 1) {
+                if (fabs(b[k] - b_prec[k]) < step_min) active[k] = 0;
+                b[k] = b_prec[k] + (b[k] - b_prec[k]) / 2;
+                memcpy(&tmp[k * P], &x[k * P], sizeof(double) * P);
+                mparams[k * np + param_idx] = (1 - b[k]) * Rstart[k] + b[k] * goal[k];
+            } else {
+                memcpy(&tmp[k * P], &wx[a * P], sizeof(double) * P);
+                if (b[k] == 1) {
+                    active[k] = 0;
+                    memcpy(&x[k * P], &tmp[k * P], sizeof(double) * P);
+                } else {
+                    b_prec[k] = b[k];
+                    b[k] = std::min(b[k] + step, 1.0);
+                    memcpy(&x[k * P], &tmp[k * P], sizeof(double) * P);
+                    mparams[k * np + param_idx] = (1 - b[k]) * Rstart[k] + b[k] * goal[k];
+                }
+            }
+        }
+    }
+    return SOCP_OK;
+}
+
+int socp_continuation_boundary_batch(socp_ctx *ctx, const socp_shape *shape, long B,
+                                     const double *mparams, const double *time_prec,
+                                     const double *Xb_prec, const double *time_des,
+                                     const double *Xb_des, double *x, double xtol, int maxfev,
+                                     double step, double step_min, int *info, int *calls) {
+    int rc = check_problem_args(ctx, shape, B, mparams, time_prec, Xb_prec, x, info);
+    if (rc != SOCP_OK) return rc;
+    if (!time_des || !Xb_des) return fail(ctx, SOCP_ERR_ARG, "NULL desired boundary data");
+    const int P = socp_num_param(shape), dim = kDim[shape->model_id], np = kNP[shape->model_id], M = shape->num_multi;
+    const int nt = M + 1, nx = (M + 1) * dim;
+    if (step <= 0) return fail(ctx, SOCP_ERR_ARG, "continuation step must be > 0 (use socp_solve_batch otherwise)");
+    std::vector<double> b(B), b_prec(B, 0.0), tmp((size_t)B * P);
+    std::vector<char> active(B, 1);
+    for (long k = 0; k < B; ++k) {
+        b[k] = std::min(step, 1.0);
+        info[k] = 0;
+        if (calls) { calls[2 * k] = 0; calls[2 * k + 1] = 0; }
+    }
+    memcpy(tmp.data(), x, sizeof(double) * (size_t)B * P);
+    std::vector<long> idx;
+    std::vector<double> wx, wmp, wtime, wXb, wfn;
+    std::vector<int> winfo, wnfev;
+    for (;;) {
+        idx.clear();
+        for (long k = 0; k < B; ++k) if (active[k]) idx.push_back(k);
+        if (idx.empty()) break;
+        const long A = (long)idx.size();
+        wx.resize((size_t)A * P); wmp.resize((size_t)A * np); wtime.resize((size_t)A * nt); wXb.resize((size_t)A * nx);
+        winfo.resize(A); wnfev.resize(A); wfn.resize(A);
+        for (long a = 0; a < A; ++a) {
+            const long k = idx[a];
+            const double bk = b[k];
+            memcpy(&wx[a * P], &tmp[k * P], sizeof(double) * P);
+            memcpy(&wmp[a * np], &mparams[k * np], sizeof(double) * np);
+            for (int i = 0; i < nt; ++i) wtime[a * nt + i] = (1 - bk) * time_prec[k * nt + i] + bk * time_des[k * nt + i];
+            for (int i = 0; i < nx; ++i) wXb[a * nx + i] = (1 - bk) * Xb_prec[k * nx + i] + bk * Xb_des[k * nx + i];
+        }
+        rc = socp_solve_batch(ctx, shape, A, wmp.data(), wtime.data(), wXb.data(), wx.data(), xtol, maxfev,
+                              winfo.data(), wnfev.data(), wfn.data(), SOCP_HOST);
+        if (rc != SOCP_OK) return rc;
+        for (long a = 0; a < A; ++a) {
+            const long k = idx[a];
+            const int ret = winfo[a];
+            info[k] = ret;
+            if (calls) { calls[2 * k] += 1; calls[2 * k + 1] += wnfev[a]; }
+            if (ret != 1) {
+                if (fabs(b[k] - b_prec[k]) < step_min) active[k] = 0;
+                b[k] = b_prec[k] + (b[k] - b_prec[k]) / 2;
+                memcpy(&tmp[k * P], &x[k * P], sizeof(double) * P);
+            } else {
+                memcpy(&tmp[k * P], &wx[a * P], sizeof(double) * P);
+                memcpy(&x[k * P], &tmp[k * P], sizeof(double) * P);
+                if (b[k] == 1) active[k] = 0;
+                else { b_prec[k] = b[k]; b[k] = std::min(b[k] + step, 1.0); }
+            }
+        }
+    }
+    return SOCP_OK;
+}
+
+}  // extern "C"
