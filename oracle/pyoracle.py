@@ -33,7 +33,8 @@ class Problem(ctypes.Structure):
                 ("Xb", (ctypes.c_double * MAX_DIM) * MAX_NODES),
                 ("obs", ctypes.POINTER(Obstacles)),
                 ("sw", ctypes.c_double * MAX_NODES), ("nsw", ctypes.c_int),
-                ("chart", ctypes.c_int), ("stage", ctypes.c_int), ("rk4_steps", ctypes.c_long)]
+                ("chart", ctypes.c_int), ("stage", ctypes.c_int), ("rk4_steps", ctypes.c_long),
+                ("noise_ulps", ctypes.c_double), ("noise_state", ctypes.c_ulonglong)]
 
 
 _SIGS = False

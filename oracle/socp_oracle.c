@@ -407,6 +407,24 @@ static double vtol_H(const so_problem *p, const double *X)
         + (p_vx * (a_max * u[0] - ca * vx * normV) + p_vy * (a_max * u[1] - ca * vy * normV) + p_vz * (a_max * u[2] - ca * vz * normV));
 }
 
+/* conditioning probe: uniform [-1,1] (tests only, see socp_oracle.h) */
+static double noise_u(so_problem *p)
+{
+    p->noise_state = p->noise_state * 6364136223846793005ULL + 1442695040888963407ULL;
+    return ((double)(p->noise_state >> 11) / 9007199254740992.0) * 2.0 - 1.0;
+}
+/* the argument of acos() in the chart conversions sits next to 1, where acos turns 1 ulp into
+ * sqrt(ulp): the probe perturbs it like everything else */
+static double noisy_unit(so_problem *p, double a)
+{
+    if (p && p->noise_ulps > 0) {
+        a *= 1.0 + p->noise_ulps * 1.1102230246251565e-16 * noise_u(p);
+        if (a > 1.0) a = 1.0;
+        if (a < -1.0) a = -1.0;
+    }
+    return a;
+}
+
 /* ==================== interceptor (src/models/interceptor/interceptor.cpp) =============== */
 
 /* interceptor.cpp:984-999 */
@@ -682,7 +700,7 @@ static void icp_costate_transport(double Jfrom[6][6], double Jto[6][6], const do
 }
 
 /* interceptor.cpp:622-727 */
-static void icp_convert_12(const double *X1, double *X2)
+static void icp_convert_12(so_problem *p, const double *X1, double *X2)
 {
     const double eps = 1e-18;
     for (int i = 0; i < 12; ++i) X2[i] = X1[i];
@@ -691,14 +709,15 @@ static void icp_convert_12(const double *X1, double *X2)
     if (gamma == M_PI / 2.0) { X2[2] = 0; X2[3] = -M_PI; }
     else if (gamma == -M_PI / 2.0) { X2[2] = 0; X2[3] = 0; }
     else {
-        X2[2] = acos(sqrt(sin(gamma) * sin(gamma) + cos(gamma) * cos(gamma) * cos(chi) * cos(chi)));
+        double arg = noisy_unit(p, sqrt(sin(gamma) * sin(gamma) + cos(gamma) * cos(gamma) * cos(chi) * cos(chi)));
+        X2[2] = acos(arg);
         if (cos(gamma) * sin(chi) < 0)
-            X2[2] = -acos(sqrt(sin(gamma) * sin(gamma) + cos(gamma) * cos(gamma) * cos(chi) * cos(chi)));
+            X2[2] = -acos(arg);
         double sinPhi = cos(gamma) * cos(chi) / cos(X2[2]);
         if (fabs(sinPhi) < eps && sin(gamma) / cos(X2[2]) < 0) X2[3] = 0;
         else if (fabs(sinPhi) < eps && sin(gamma) / cos(X2[2]) > 0) X2[3] = -M_PI;
-        else if (sinPhi > 0) X2[3] = acos(-sin(gamma) / cos(X2[2]));
-        else X2[3] = -acos(-sin(gamma) / cos(X2[2]));
+        else if (sinPhi > 0) X2[3] = acos(noisy_unit(p, -sin(gamma) / cos(X2[2])));
+        else X2[3] = -acos(noisy_unit(p, -sin(gamma) / cos(X2[2])));
     }
     double J1[6][6], J2[6][6];
     icp_jac1(J1, L, l, r, v, gamma, chi);
@@ -707,7 +726,7 @@ static void icp_convert_12(const double *X1, double *X2)
 }
 
 /* interceptor.cpp:730-841 */
-static void icp_convert_21(const double *X2, double *X1)
+static void icp_convert_21(so_problem *p, const double *X2, double *X1)
 {
     const double eps = 1e-18;
     for (int i = 0; i < 12; ++i) X1[i] = X2[i];
@@ -716,14 +735,15 @@ static void icp_convert_21(const double *X2, double *X1)
     if (theta == M_PI / 2.0) { X1[2] = 0; X1[3] = M_PI / 2.0; }
     else if (theta == -M_PI / 2.0) { X1[2] = 0; X1[3] = -M_PI / 2.0; }
     else {
-        X1[2] = acos(sqrt(sin(theta) * sin(theta) + cos(theta) * cos(theta) * sin(phi) * sin(phi)));
+        double arg = noisy_unit(p, sqrt(sin(theta) * sin(theta) + cos(theta) * cos(theta) * sin(phi) * sin(phi)));
+        X1[2] = acos(arg);
         if (cos(theta) * cos(phi) > 0)
-            X1[2] = -acos(sqrt(sin(theta) * sin(theta) + cos(theta) * cos(theta) * sin(phi) * sin(phi)));
+            X1[2] = -acos(arg);
         double sinChi = sin(theta) / cos(X1[2]);
         if (fabs(sinChi) < eps && sin(phi) * cos(theta) / cos(X1[2]) > 0) X1[3] = 0;
         else if (fabs(sinChi) < eps && sin(phi) * cos(theta) / cos(X1[2]) < 0) X1[3] = -M_PI;
-        else if (sinChi > 0) X1[3] = acos(sin(phi) * cos(theta) / cos(X1[2]));
-        else X1[3] = -acos(sin(phi) * cos(theta) / cos(X1[2]));
+        else if (sinChi > 0) X1[3] = acos(noisy_unit(p, sin(phi) * cos(theta) / cos(X1[2])));
+        else X1[3] = -acos(noisy_unit(p, sin(phi) * cos(theta) / cos(X1[2])));
     }
     double J1[6][6], J2[6][6];
     icp_jac1(J1, L, l, r, v, X1[2], X1[3]);
@@ -736,14 +756,24 @@ static void icp_set_chart(so_problem *p, double *X)
 {
     if (fabs(cos(X[2])) >= I_CHART_LIMIT) return;
     double Y[12];
-    if (p->chart == 1) { icp_convert_12(X, Y); p->chart = 2; }
-    else { icp_convert_21(X, Y); p->chart = 1; }
+    if (p->chart == 1) { icp_convert_12(p, X, Y); p->chart = 2; }
+    else { icp_convert_21(p, X, Y); p->chart = 1; }
     memcpy(X, Y, sizeof Y);
 }
 
 /* ================================ dispatch ============================================== */
 
+static void so_rhs_exact(so_problem *p, double t, const double *X, double *dX);
+
 void so_rhs(so_problem *p, double t, const double *X, double *dX)
+{
+    so_rhs_exact(p, t, X, dX);
+    if (p->noise_ulps > 0)
+        for (int i = 0; i < 2 * p->dim; ++i)
+            dX[i] *= 1.0 + p->noise_ulps * 1.1102230246251565e-16 * noise_u(p);
+}
+
+static void so_rhs_exact(so_problem *p, double t, const double *X, double *dX)
 {
     switch (p->model_id) {
     case SO_GODDARD: goddard_rhs(p, t, X, dX); break;
@@ -853,7 +883,7 @@ void so_traj(so_problem *p, double t0, const double *X0, double tf, double *Xf)
         }
         if (p->chart == 2) {
             double Y[12];
-            icp_convert_21(X, Y);
+            icp_convert_21(p, X, Y);
             memcpy(X, Y, sizeof Y);
         }
     }

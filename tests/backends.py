@@ -56,9 +56,11 @@ class OracleBackend:
         p.set_boundary(spec["time"], spec["Xb"])
         return p
 
-    def traj(self, model, mparams, t0, X0, tf, steps=None, sw=None):
+    def traj(self, model, mparams, t0, X0, tf, steps=None, sw=None, noise_ulps=0.0, seed=1):
         p = O.OracleProblem(model, 1, step_nbr=steps,
                             obstacles=oracle_obstacles() if model == S.VTOL else None)
+        p.p.noise_ulps = noise_ulps
+        p.p.noise_state = seed
         for k, v in enumerate(mparams):
             p.set_param(k, v)
         if sw is not None:
