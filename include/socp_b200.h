@@ -69,6 +69,10 @@ typedef struct {
     double kernel_launches;  /* kernels of this library launched since the last reset */
     double solver_rounds;    /* lock-step rounds of the batched Powell-hybrid state machine */
     double device_bytes;     /* workspace currently held on the device */
+    /* filled only while profiling is on (socp_set_profiling): CUDA-event time of the two kernels
+     * of the solver rounds, on the context stream */
+    double integrate_ms, integrate_launches;   /* integrate_worklist */
+    double advance_ms, advance_launches;       /* advance (assembly + Powell-hybrid step) */
 } socp_stats;
 
 /* ---- context ------------------------------------------------------------------------------ */
@@ -79,6 +83,8 @@ int socp_set_stream(socp_ctx *ctx, void *cuda_stream); /* run on a caller-owned 
 int socp_sync(socp_ctx *ctx);
 int socp_get_stats(socp_ctx *ctx, socp_stats *out);
 int socp_reset_stats(socp_ctx *ctx);
+/* per-kernel CUDA-event timing of the solver rounds (adds two event records per launch) */
+int socp_set_profiling(socp_ctx *ctx, int on);
 /* wall-clock-free timing of the library's own kernels: CUDA events on the context stream */
 int socp_timer_start(socp_ctx *ctx);
 int socp_timer_stop(socp_ctx *ctx, float *ms);

@@ -21,13 +21,15 @@ class Shape(ctypes.Structure):
 
 class Stats(ctypes.Structure):
     _fields_ = [("rk4_steps", ctypes.c_double), ("kernel_launches", ctypes.c_double),
-                ("solver_rounds", ctypes.c_double), ("device_bytes", ctypes.c_double)]
+                ("solver_rounds", ctypes.c_double), ("device_bytes", ctypes.c_double),
+                ("integrate_ms", ctypes.c_double), ("integrate_launches", ctypes.c_double),
+                ("advance_ms", ctypes.c_double), ("advance_launches", ctypes.c_double)]
 
 
 _LIB = None
 # every symbol include/socp_b200.h declares
 SYMBOLS = ["socp_create", "socp_destroy", "socp_last_error", "socp_set_stream", "socp_sync",
-           "socp_get_stats", "socp_reset_stats", "socp_timer_start", "socp_timer_stop",
+           "socp_get_stats", "socp_reset_stats", "socp_set_profiling", "socp_timer_start", "socp_timer_stop",
            "socp_model_dim", "socp_model_nparams", "socp_model_default_steps",
            "socp_model_default_params", "socp_num_param", "socp_set_obstacles", "socp_traj_batch",
            "socp_point_batch", "socp_residual_batch", "socp_fdjac_batch", "socp_solve_batch",
@@ -55,6 +57,7 @@ def lib():
     L.socp_sync.argtypes = [vp]
     L.socp_get_stats.argtypes = [vp, P(Stats)]
     L.socp_reset_stats.argtypes = [vp]
+    L.socp_set_profiling.argtypes = [vp, ci]
     L.socp_timer_start.argtypes = [vp]
     L.socp_timer_stop.argtypes = [vp, P(ctypes.c_float)]
     L.socp_model_dim.argtypes = [ci]

@@ -50,6 +50,9 @@ struct socp_ctx {
     double steps_base = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int sm_count = 0;
+    int profile = 0;
+    double integrate_ms = 0, integrate_launches = 0, advance_ms = 0, advance_launches = 0;
+    std::vector<cudaEvent_t> prof_events;
     SolverWorkspace solver;              // persistent state of the batched solver (solver.cuh)
 };
 
@@ -198,6 +201,7 @@ void socp_destroy(socp_ctx *ctx) {
     if (ctx->d_counters) cudaFree(ctx->d_counters);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    for (auto e : ctx->prof_events) cudaEventDestroy(e);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -230,6 +234,8 @@ int socp_get_stats(socp_ctx *ctx, socp_stats *out) {
     double bytes = 0;
     for (auto &b : ctx->pool) bytes += (double)b.cap;
     out->device_bytes = bytes + ctx->solver.bytes();
+    out->integrate_ms = ctx->integrate_ms; out->integrate_launches = ctx->integrate_launches;
+    out->advance_ms = ctx->advance_ms; out->advance_launches = ctx->advance_launches;
     return SOCP_OK;
 }
 
@@ -238,6 +244,13 @@ int socp_reset_stats(socp_ctx *ctx) {
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
     ctx->launches = 0;
     ctx->rounds = 0;
+    ctx->integrate_ms = ctx->integrate_launches = ctx->advance_ms = ctx->advance_launches = 0;
+    return SOCP_OK;
+}
+
+int socp_set_profiling(socp_ctx *ctx, int on) {
+    if (!ctx) return SOCP_ERR_ARG;
+    ctx->profile = on ? 1 : 0;
     return SOCP_OK;
 }
 

@@ -94,22 +94,47 @@ size_t carve(HostPlan &pl, void *blob, long Bw) {
     return c.off + 256;
 }
 
+const int kProfSlots = 16;      // rounds between two harvests of the profiling events
+
+cudaEvent_t prof_event(socp_ctx *ctx, int idx) {
+    while ((int)ctx->prof_events.size() <= idx) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        ctx->prof_events.push_back(e);
+    }
+    return ctx->prof_events[idx];
+}
+
+// accumulate the per-kernel times of the last `n` profiled rounds (events must have completed)
+void prof_harvest(socp_ctx *ctx, int n) {
+    for (int k = 0; k < n; ++k) {
+        float a = 0, b = 0;
+        cudaEventElapsedTime(&a, ctx->prof_events[3 * k], ctx->prof_events[3 * k + 1]);
+        cudaEventElapsedTime(&b, ctx->prof_events[3 * k + 1], ctx->prof_events[3 * k + 2]);
+        ctx->integrate_ms += a; ctx->integrate_launches += 1;
+        ctx->advance_ms += b; ctx->advance_launches += 1;
+    }
+}
+
 template <int MODEL>
-void launch_round(socp_ctx *ctx, const SolverDev &D, int cur, int grid_int, int grid_adv) {
+void launch_round(socp_ctx *ctx, const SolverDev &D, int cur, int grid_int, int grid_adv, int prof_slot) {
+    if (prof_slot >= 0) cudaEventRecord(prof_event(ctx, 3 * prof_slot), ctx->stream);
     integrate_worklist<MODEL><<<grid_int, 128, 0, ctx->stream>>>(D, cur);
+    if (prof_slot >= 0) cudaEventRecord(prof_event(ctx, 3 * prof_slot + 1), ctx->stream);
     if (D.P <= 32) advance<MODEL, 32><<<grid_adv, 128, 0, ctx->stream>>>(D, cur);
     else advance<MODEL, 128><<<grid_adv, 128, 0, ctx->stream>>>(D, cur);
+    if (prof_slot >= 0) cudaEventRecord(prof_event(ctx, 3 * prof_slot + 2), ctx->stream);
     ctx->launches += 2;
     ctx->rounds += 1;
 }
 
-void launch_round_any(socp_ctx *ctx, const SolverDev &D, int cur, int gi, int ga) {
+void launch_round_any(socp_ctx *ctx, const SolverDev &D, int cur, int gi, int ga, int ps) {
     switch (D.model_id) {
-    case SOCP_GODDARD: launch_round<GODDARD>(ctx, D, cur, gi, ga); break;
-    case SOCP_DOUBLE_INTEGRATOR: launch_round<DOUBLE_INTEGRATOR>(ctx, D, cur, gi, ga); break;
-    case SOCP_COVID19: launch_round<COVID19>(ctx, D, cur, gi, ga); break;
-    case SOCP_VTOL_UAV: launch_round<VTOL_UAV>(ctx, D, cur, gi, ga); break;
-    case SOCP_INTERCEPTOR: launch_round<INTERCEPTOR>(ctx, D, cur, gi, ga); break;
+    case SOCP_GODDARD: launch_round<GODDARD>(ctx, D, cur, gi, ga, ps); break;
+    case SOCP_DOUBLE_INTEGRATOR: launch_round<DOUBLE_INTEGRATOR>(ctx, D, cur, gi, ga, ps); break;
+    case SOCP_COVID19: launch_round<COVID19>(ctx, D, cur, gi, ga, ps); break;
+    case SOCP_VTOL_UAV: launch_round<VTOL_UAV>(ctx, D, cur, gi, ga, ps); break;
+    case SOCP_INTERCEPTOR: launch_round<INTERCEPTOR>(ctx, D, cur, gi, ga, ps); break;
     }
 }
 
@@ -158,7 +183,7 @@ int run_solver(socp_ctx *ctx, const socp_shape *shape, long B, const double *d_m
     D.counters = ctx->d_counters;
     const int grid_int = ctx->sm_count * 8;
     const int grid_adv = ctx->sm_count * 8;
-    const int check_every = (run_mode == RUN_SOLVE) ? 8 : 1;
+    const int check_every = (run_mode == RUN_SOLVE) ? 8 : 1;   // <= kProfSlots
     const long max_rounds = (run_mode == RUN_SOLVE) ? (long)maxfev + 8 : (run_mode == RUN_FDJAC ? 2 : 1);
 
     for (long first = 0; first < B; first += wave) {
@@ -170,16 +195,23 @@ int run_solver(socp_ctx *ctx, const socp_shape *shape, long B, const double *d_m
         const long nthreads = Bw * D.P;
         solver_init<<<(unsigned)((nthreads + 255) / 256), 256, 0, ctx->stream>>>(D, d_x_in, first);
         ctx->launches += 1;
-        int cur = 0;
+        int cur = 0, pending = 0;
         for (long round = 0; round < max_rounds; ++round) {
-            launch_round_any(ctx, D, cur, grid_int, grid_adv);
+            launch_round_any(ctx, D, cur, grid_int, grid_adv, ctx->profile ? pending : -1);
+            ++pending;
             cur = 1 - cur;
             if (run_mode == RUN_SOLVE && (round % check_every) == check_every - 1) {
                 CUDA_TRY(ctx, cudaMemcpyAsync(ctx->solver.h_counts, D.counts, 4 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
                 CUDA_TRY(ctx, cudaEventRecord(ctx->solver.ev, ctx->stream));
                 CUDA_TRY(ctx, cudaEventSynchronize(ctx->solver.ev));
+                if (ctx->profile) prof_harvest(ctx, pending);
+                pending = 0;
                 if (ctx->solver.h_counts[cur * 2] + ctx->solver.h_counts[cur * 2 + 1] == 0) break;
             }
+        }
+        if (ctx->profile && pending > 0) {
+            CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+            prof_harvest(ctx, pending);
         }
         const long nfin = std::max<long>(nthreads, d_fjac_out ? Bw * (long)D.P * D.P : 0);
         solver_finish<<<(unsigned)((nfin + 255) / 256), 256, 0, ctx->stream>>>(D, first, d_x_out, d_fvec_out, d_fjac_out, d_info, d_nfev, d_fnorm);

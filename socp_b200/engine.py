@@ -141,7 +141,12 @@ class Engine:
         s = Stats()
         self._check(self._L.socp_get_stats(self._h, ctypes.byref(s)))
         return dict(rk4_steps=s.rk4_steps, kernel_launches=s.kernel_launches,
-                    solver_rounds=s.solver_rounds, device_bytes=s.device_bytes)
+                    solver_rounds=s.solver_rounds, device_bytes=s.device_bytes,
+                    integrate_ms=s.integrate_ms, integrate_launches=s.integrate_launches,
+                    advance_ms=s.advance_ms, advance_launches=s.advance_launches)
+
+    def set_profiling(self, on=True):
+        self._check(self._L.socp_set_profiling(self._h, int(bool(on))))
 
     def reset_stats(self):
         self._check(self._L.socp_reset_stats(self._h))

@@ -72,8 +72,11 @@ class OracleBackend:
     def residual(self, spec, x=None):
         return self.problem(spec).residual(spec["x0"] if x is None else x)
 
-    def fdjac(self, spec, x=None):
-        return self.problem(spec).fdjac(spec["x0"] if x is None else x)
+    def fdjac(self, spec, x=None, noise_ulps=0.0, seed=1):
+        p = self.problem(spec)
+        p.p.noise_ulps = noise_ulps
+        p.p.noise_state = seed
+        return p.fdjac(spec["x0"] if x is None else x)
 
     def solve(self, spec, maxfev=10000):
         return self.problem(spec).solve(spec["x0"], xtol=spec["xtol"], maxfev=maxfev)

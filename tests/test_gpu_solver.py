@@ -64,18 +64,20 @@ def test_fdjac_vs_oracle(oracle_lib, name):
     mask = structural_mask(spec)
     assert np.all(want[~mask] == 0.0)
     assert np.all(got[~mask] == 0.0)
-    # everything else: forward differences amplify rounding-level differences of F (a few ulp of
-    # the residual's magnitude) by 1/h_j, h_j = sqrt(1e-15)|x_j|
-    x0 = np.array(spec["x0"])
-    h = np.sqrt(1e-15) * np.abs(x0)
-    h[h == 0] = np.sqrt(1e-15)
-    f = np.abs(ora.residual(spec))
-    fscale = np.maximum(f, 1e-3 * max(np.max(f), np.max(np.abs(x0)), 1.0))
+    # everything else: forward differences amplify rounding-level differences of F by 1/h_j
+    # (h_j = sqrt(1e-15)|x_j|).  The admissible difference is measured on the oracle itself: its FD
+    # Jacobian is recomputed with every RHS evaluation perturbed by a random +-8 ulp (the accuracy
+    # class of CUDA libm + FMA contraction); the bound is 4x the largest deviation of 3 such runs.
+    dev = np.zeros_like(want)
+    for seed in (1, 2, 3):
+        dev = np.maximum(dev, np.abs(ora.fdjac(spec, noise_ulps=8.0, seed=seed) - want))
     colmax = np.max(np.abs(want), axis=0)
-    tol = 64 * 2.2e-16 * fscale[:, None] / h[None, :] + 1e-6 * colmax[None, :]
+    tol = 4 * dev + 1e-9 * colmax[None, :]
     bad = np.abs(got - want) > tol
     assert not np.any(bad), "%s: %d FD-Jacobian entries differ beyond rounding amplification (worst %.3e)" % (
-        name, bad.sum(), np.max(np.abs(got - want) / tol))
+        name, bad.sum(), np.max(np.abs(got - want)[bad] / tol[bad]))
+    rel = np.max(np.abs(got - want) / np.maximum(colmax[None, :], 1e-300))
+    print("%s: FD Jacobian column-relative difference %.2e" % (name, rel))
 
 
 DEMO_SOLVES = ["di_free_tf", "goddard_stage1", "goddard_stage4_singular", "covid_stage1", "interceptor_init",
