@@ -72,7 +72,8 @@ typedef struct {
     /* filled only while profiling is on (socp_set_profiling): CUDA-event time of the two kernels
      * of the solver rounds, on the context stream */
     double integrate_ms, integrate_launches;   /* integrate_worklist */
-    double advance_ms, advance_launches;       /* advance (assembly + Powell-hybrid step) */
+    double advance_ms, advance_launches;       /* hybrd_res_kernel + hybrd_jac_kernel (Powell-hybrid step) */
+    double assemble_ms;                        /* assemble_kernel (residual / FD Jacobian assembly) */
 } socp_stats;
 
 /* ---- context ------------------------------------------------------------------------------ */

@@ -23,7 +23,8 @@ class Stats(ctypes.Structure):
     _fields_ = [("rk4_steps", ctypes.c_double), ("kernel_launches", ctypes.c_double),
                 ("solver_rounds", ctypes.c_double), ("device_bytes", ctypes.c_double),
                 ("integrate_ms", ctypes.c_double), ("integrate_launches", ctypes.c_double),
-                ("advance_ms", ctypes.c_double), ("advance_launches", ctypes.c_double)]
+                ("advance_ms", ctypes.c_double), ("advance_launches", ctypes.c_double),
+                ("assemble_ms", ctypes.c_double)]
 
 
 _LIB = None

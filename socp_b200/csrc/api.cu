@@ -8,6 +8,7 @@
 #include <string>
 #include <vector>
 #include <algorithm>
+#include <map>
 
 #include "../../include/socp_b200.h"
 #include "models.cuh"
@@ -51,7 +52,7 @@ struct socp_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int sm_count = 0;
     int profile = 0;
-    double integrate_ms = 0, integrate_launches = 0, advance_ms = 0, advance_launches = 0;
+    double integrate_ms = 0, integrate_launches = 0, advance_ms = 0, advance_launches = 0, assemble_ms = 0;
     std::vector<cudaEvent_t> prof_events;
     SolverWorkspace solver;              // persistent state of the batched solver (solver.cuh)
 };
@@ -236,6 +237,7 @@ int socp_get_stats(socp_ctx *ctx, socp_stats *out) {
     out->device_bytes = bytes + ctx->solver.bytes();
     out->integrate_ms = ctx->integrate_ms; out->integrate_launches = ctx->integrate_launches;
     out->advance_ms = ctx->advance_ms; out->advance_launches = ctx->advance_launches;
+    out->assemble_ms = ctx->assemble_ms;
     return SOCP_OK;
 }
 
@@ -244,7 +246,7 @@ int socp_reset_stats(socp_ctx *ctx) {
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
     ctx->launches = 0;
     ctx->rounds = 0;
-    ctx->integrate_ms = ctx->integrate_launches = ctx->advance_ms = ctx->advance_launches = 0;
+    ctx->integrate_ms = ctx->integrate_launches = ctx->advance_ms = ctx->advance_launches = ctx->assemble_ms = 0;
     return SOCP_OK;
 }
 

@@ -345,18 +345,66 @@ __device__ __noinline__ void assemble(const SolverDev &D, long b, int col, doubl
     }
 }
 
+// ---- kernel 2a: assemble residuals and forward-difference Jacobian columns ----------------------
+// One thread per residual request, one thread per (Jacobian request, column).  This is the only
+// solver kernel besides integrate_worklist that contains model code.
+template <int MODEL>
+__global__ void __launch_bounds__(128)
+assemble_kernel(SolverDev D, int cur) {
+    const int nres = D.counts[cur * 2 + 0], njac = D.counts[cur * 2 + 1];
+    const int *res_list = D.lists + (size_t)(cur * 2 + 0) * D.B;
+    const int *jac_list = D.lists + (size_t)(cur * 2 + 1) * D.B;
+    const int n = D.P;
+    const long total = (long)nres + (long)njac * n;
+    for (long w = (long)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += (long)gridDim.x * blockDim.x) {
+        if (w < nres) {
+            const long b = res_list[w];
+            const int *is = D.istate + b * I_COUNT;
+            const int trial = 1 - is[I_BASE];
+            const double *te = D.ends + ((b * 2 + trial) * D.M) * D.REC;
+            double *out = (is[I_PHASE] == PH_F0) ? D.fvec + b * n : D.wa4 + b * n;
+            assemble<MODEL>(D, b, -1, 0.0, te, D.jends + (size_t)b * D.nJ * D.REC, out);
+        } else {
+            const long w2 = w - nres;
+            const long b = jac_list[w2 / n];
+            const int j = (int)(w2 % n);
+            const int *is = D.istate + b * I_COUNT;
+            const double *be = D.ends + ((b * 2 + is[I_BASE]) * D.M) * D.REC;
+            const double h = fd_step(D.xe[b * n + j], D.epsfcn);
+            double *colj = D.fjac + (size_t)b * n * n + (size_t)j * n;
+            const double *fvec = D.fvec + b * n;
+            assemble<MODEL>(D, b, j, h, be, D.jends + (size_t)b * D.nJ * D.REC, colj);
+            for (int i = 0; i < n; ++i) colj[i] = (colj[i] - fvec[i]) / h;      // fdjac1
+        }
+    }
+}
+
 // ---- MINPACK linear algebra on a thread group --------------------------------------------------
-// Matrices are column-major with leading dimension n (cminpack convention); r is the packed upper
-// triangle stored by rows.  Every routine starts and ends with a group barrier.
+// Q (fjac) is column-major with leading dimension ldq, r is the packed upper triangle stored by
+// rows (cminpack conventions).  The pointers may be shared or global memory.  Thread mappings are
+// chosen so that a group touches consecutive addresses (coalesced in HBM, conflict-free in shared
+// memory when ldq is odd).  Every routine starts and ends with a group barrier.
+
+template <int G> SOCP_DEV void gcopy(double *dst, const double *src, int n) {
+    for (int i = threadIdx.x % G; i < n; i += G) dst[i] = src[i];
+}
+
+SOCP_DEV double warp_sum(double v) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    return v;
+}
+
+SOCP_DEV int rowstart(int n, int j) { return j * n - (j * (j - 1)) / 2; }
 
 // qrfac (no pivoting) fused with "qtf = Q^T fvec" (the Householder reflections are applied to
-// qtf as one more column); rdiag/acnorm as in MINPACK.
+// qtf as one more column); rdiag/acnorm as in MINPACK.  One thread per column.
 template <int G>
-__device__ void qrfac_g(int n, double *a, double *rdiag, double *acnorm, double *qtf, double *red) {
+__device__ void qrfac_g(int n, double *a, int lda, double *rdiag, double *acnorm, double *qtf, double *red) {
     const int tid = threadIdx.x % G;
     gsync<G>();
     for (int j = tid; j < n; j += G) {                 // column norms
-        const double *cj = a + (size_t)j * n;
+        const double *cj = a + (size_t)j * lda;
         double s2 = 0;
         bool odd = false;
         for (int i = 0; i < n; ++i) {
@@ -368,7 +416,7 @@ __device__ void qrfac_g(int n, double *a, double *rdiag, double *acnorm, double 
     }
     gsync<G>();
     for (int j = 0; j < n; ++j) {
-        double *cj = a + (size_t)j * n;
+        double *cj = a + (size_t)j * lda;
         double ajnorm = enorm_g<G>(n - j, cj + j, red);
         if (ajnorm != 0.) {
             if (cj[j] < 0.) ajnorm = -ajnorm;
@@ -381,7 +429,7 @@ __device__ void qrfac_g(int n, double *a, double *rdiag, double *acnorm, double 
             gsync<G>();
             const double ajj = cj[j];
             for (int k = j + 1 + tid; k <= n; k += G) {  // remaining columns, and qtf as column n
-                double *ck = (k < n) ? a + (size_t)k * n : qtf;
+                double *ck = (k < n) ? a + (size_t)k * lda : qtf;
                 double sum = 0.;
                 for (int i = j; i < n; ++i) sum += cj[i] * ck[i];
                 const double temp = sum / ajj;
@@ -395,11 +443,11 @@ __device__ void qrfac_g(int n, double *a, double *rdiag, double *acnorm, double 
 
 // copy R into packed storage (upper triangle by rows), diagonal from rdiag
 template <int G>
-__device__ void pack_r_g(int n, const double *a, const double *rdiag, double *r) {
+__device__ void pack_r_g(int n, const double *a, int lda, const double *rdiag, double *r) {
     const int tid = threadIdx.x % G;
     for (int j = tid; j < n; j += G) {
         int l = j;
-        for (int i = 0; i < j; ++i) { r[l] = a[i + (size_t)j * n]; l += n - 1 - i; }
+        for (int i = 0; i < j; ++i) { r[l] = a[i + (size_t)j * lda]; l += n - 1 - i; }
         r[l] = rdiag[j];
     }
     gsync<G>();
@@ -407,20 +455,20 @@ __device__ void pack_r_g(int n, const double *a, const double *rdiag, double *r)
 
 // qform: accumulate Q (n x n) in place from the Householder vectors; wa is scratch [n]
 template <int G>
-__device__ void qform_g(int n, double *q, double *wa) {
+__device__ void qform_g(int n, double *q, int lda, double *wa) {
     const int tid = threadIdx.x % G;
     for (int j = 1 + tid; j < n; j += G)
-        for (int i = 0; i < j; ++i) q[i + (size_t)j * n] = 0.;
+        for (int i = 0; i < j; ++i) q[i + (size_t)j * lda] = 0.;
     gsync<G>();
     for (int l = 0; l < n; ++l) {
         const int k = n - 1 - l;
-        double *ck = q + (size_t)k * n;
+        double *ck = q + (size_t)k * lda;
         for (int i = k + tid; i < n; i += G) { wa[i] = ck[i]; ck[i] = (i == k) ? 1. : 0.; }
         gsync<G>();
         const double wk = wa[k];
         if (wk != 0.) {
             for (int j = k + tid; j < n; j += G) {
-                double *cj = q + (size_t)j * n;
+                double *cj = q + (size_t)j * lda;
                 double sum = 0.;
                 for (int i = k; i < n; ++i) sum += cj[i] * wa[i];
                 const double temp = sum / wk;
@@ -431,37 +479,55 @@ __device__ void qform_g(int n, double *q, double *wa) {
     }
 }
 
+// y[i] = add[i] + sum_{j >= i} R(i,j) v[j]   (one warp per row, lanes along the packed row)
+template <int G>
+__device__ void rmulv_g(int n, const double *r, const double *v, const double *add, double *y) {
+    const int lane = threadIdx.x & 31, warp = (threadIdx.x % G) >> 5;
+    gsync<G>();
+    for (int i = warp; i < n; i += G / 32) {
+        const double *ri = r + rowstart(n, i);
+        double part = 0.;
+        for (int j = i + lane; j < n; j += 32) part += ri[j - i] * v[j];
+        const double s = warp_sum(part);
+        if (lane == 0) y[i] = (add ? add[i] : 0.) + s;
+    }
+    gsync<G>();
+}
+
 // dogleg: x <- step; wa1, wa2 scratch
 template <int G>
 __device__ void dogleg_g(int n, const double *r, const double *diag, const double *qtb, double delta,
                          double *x, double *wa1, double *wa2, double *red) {
     const int tid = threadIdx.x % G;
+    const int lane = threadIdx.x & 31;
     gsync<G>();
-    // Gauss-Newton direction: back substitution, row by row from the bottom
-    for (int k = 1; k <= n; ++k) {
-        const int j = n - k;
-        const int jj = j * n - (j * (j - 1)) / 2;            // index of r(j,j)
-        double part = 0.;
-        for (int i = j + 1 + tid; i < n; i += G) part += r[jj + (i - j)] * x[i];
-        const double sum = gsum<G>(part, red);
-        double temp = r[jj];
-        if (temp == 0.) {
-            int l = j;
-            for (int i = 0; i <= j; ++i) { temp = fmax(temp, fabs(r[l])); l += n - 1 - i; }
-            temp = EPSMCH * temp;
-            if (temp == 0.) temp = EPSMCH;
+    // Gauss-Newton direction: back substitution row by row from the bottom, on one warp
+    if (tid < 32) {
+        for (int j = n - 1; j >= 0; --j) {
+            const int jj = rowstart(n, j);
+            double part = 0.;
+            for (int i = j + 1 + lane; i < n; i += 32) part += r[jj + (i - j)] * x[i];
+            const double sum = warp_sum(part);
+            double temp = r[jj];
+            if (temp == 0.) {
+                int l = j;
+                for (int i = 0; i <= j; ++i) { temp = fmax(temp, fabs(r[l])); l += n - 1 - i; }
+                temp = EPSMCH * temp;
+                if (temp == 0.) temp = EPSMCH;
+            }
+            if (lane == 0) x[j] = (qtb[j] - sum) / temp;
+            __syncwarp();
         }
-        if (tid == 0) x[j] = (qtb[j] - sum) / temp;
-        gsync<G>();
     }
+    gsync<G>();
     for (int j = tid; j < n; j += G) { wa1[j] = 0.; wa2[j] = diag[j] * x[j]; }
     gsync<G>();
     const double qnorm = enorm_g<G>(n, wa2, red);
     if (qnorm <= delta) { gsync<G>(); return; }
-    // scaled gradient direction: wa1 = (R^T qtb) / diag
+    // scaled gradient direction: wa1 = (R^T qtb) / diag   (one thread per column)
     for (int i = tid; i < n; i += G) {
         double s = 0.;
-        for (int j = 0; j <= i; ++j) s += r[j * n - (j * (j - 1)) / 2 + (i - j)] * qtb[j];
+        for (int j = 0; j <= i; ++j) s += r[rowstart(n, j) + (i - j)] * qtb[j];
         wa1[i] = s / diag[i];
     }
     gsync<G>();
@@ -470,14 +536,7 @@ __device__ void dogleg_g(int n, const double *r, const double *diag, const doubl
     if (gnorm != 0.) {
         gsync<G>();
         for (int j = tid; j < n; j += G) wa1[j] = (wa1[j] / gnorm) / diag[j];
-        gsync<G>();
-        for (int j = tid; j < n; j += G) {
-            const int jj = j * n - (j * (j - 1)) / 2;
-            double s = 0.;
-            for (int i = j; i < n; ++i) s += r[jj + (i - j)] * wa1[i];
-            wa2[j] = s;
-        }
-        gsync<G>();
+        rmulv_g<G>(n, r, wa1, nullptr, wa2);
         double temp = enorm_g<G>(n, wa2, red);
         sgnorm = (gnorm / temp) / temp;
         alpha = 0.;
@@ -500,81 +559,83 @@ __device__ void dogleg_g(int n, const double *r, const double *diag, const doubl
 template <int G>
 __device__ void r1updt_g(int n, double *s, const double *u, double *v, double *w, double *cs, double *sn) {
     const int tid = threadIdx.x % G;
+    const int lane = threadIdx.x & 31;
     const double giant = DBL_MAX;
-    auto rowstart = [n](int j) { return j * n - (j * (j - 1)) / 2; };
     gsync<G>();
     // first sweep: the rotation coefficients depend on v only (scalar recurrence on v[n-1])
     if (tid == 0) {
         double vn = v[n - 1];
         for (int j = n - 2; j >= 0; --j) {
-            double c = 1., sgl = 0.;
-            if (v[j] != 0.) {
+            const double vj = v[j];
+            double c = 2., sgl = 0.;               // c == 2 marks "no rotation"
+            if (vj != 0.) {
                 double tau;
-                if (fabs(vn) < fabs(v[j])) {
-                    const double cotan = vn / v[j];
+                if (fabs(vn) < fabs(vj)) {
+                    const double cotan = vn / vj;
                     sgl = .5 / sqrt(.25 + .25 * (cotan * cotan));
                     c = sgl * cotan;
                     tau = 1.;
                     if (fabs(c) * giant > 1.) tau = 1. / c;
                 } else {
-                    const double tn = v[j] / vn;
+                    const double tn = vj / vn;
                     c = .5 / sqrt(.25 + .25 * (tn * tn));
                     sgl = c * tn;
                     tau = sgl;
                 }
-                vn = sgl * v[j] + c * vn;
+                vn = sgl * vj + c * vn;
                 v[j] = tau;
-                cs[j] = c; sn[j] = sgl;
-            } else {
-                cs[j] = 2.;            // marker: no rotation
             }
+            cs[j] = c; sn[j] = sgl;
         }
         v[n - 1] = vn;
     }
     gsync<G>();
     // apply to the columns: column i is touched by rotations j = min(i, n-2) .. 0
     for (int i = tid; i < n; i += G) {
-        double wi = (i == n - 1) ? s[rowstart(n - 1)] : 0.;
+        double wi = (i == n - 1) ? s[rowstart(n, n - 1)] : 0.;
         for (int j = (i < n - 1 ? i : n - 2); j >= 0; --j) {
-            if (cs[j] > 1.5) continue;
-            const int l = rowstart(j) + (i - j);
+            const double c = cs[j];
+            if (c > 1.5) continue;
+            const int l = rowstart(n, j) + (i - j);
             const double sl = s[l];
-            const double temp = cs[j] * sl - sn[j] * wi;
-            wi = sn[j] * sl + cs[j] * wi;
-            s[l] = temp;
+            s[l] = c * sl - sn[j] * wi;
+            wi = sn[j] * sl + c * wi;
         }
         w[i] = wi + v[n - 1] * u[i];                 // add the spike from the rank-1 update
     }
     gsync<G>();
-    // second sweep: eliminate the spike; rotation j depends on w[j] after rotations 0..j-1
-    for (int j = 0; j < n - 1; ++j) {
-        const int jj = rowstart(j);
-        const double wj = w[j], sjj = s[jj];
-        gsync<G>();
-        if (wj != 0.) {
-            double c, sgl, tau;
-            if (fabs(sjj) < fabs(wj)) {
-                const double cotan = sjj / wj;
-                sgl = .5 / sqrt(.25 + .25 * (cotan * cotan));
-                c = sgl * cotan;
-                tau = 1.;
-                if (fabs(c) * giant > 1.) tau = 1. / c;
-            } else {
-                const double tn = wj / sjj;
-                c = .5 / sqrt(.25 + .25 * (tn * tn));
-                sgl = c * tn;
-                tau = sgl;
+    // second sweep: eliminate the spike; rotation j depends on w[j] after rotations 0..j-1.
+    // Strictly sequential in j: run it on one warp (warp barriers only).
+    if (tid < 32) {
+        for (int j = 0; j < n - 1; ++j) {
+            const int jj = rowstart(n, j);
+            const double wj = w[j], sjj = s[jj];
+            __syncwarp();
+            if (wj != 0.) {
+                double c, sgl, tau;
+                if (fabs(sjj) < fabs(wj)) {
+                    const double cotan = sjj / wj;
+                    sgl = .5 / sqrt(.25 + .25 * (cotan * cotan));
+                    c = sgl * cotan;
+                    tau = 1.;
+                    if (fabs(c) * giant > 1.) tau = 1. / c;
+                } else {
+                    const double tn = wj / sjj;
+                    c = .5 / sqrt(.25 + .25 * (tn * tn));
+                    sgl = c * tn;
+                    tau = sgl;
+                }
+                for (int i = j + lane; i < n; i += 32) {
+                    const int l = jj + (i - j);
+                    const double sl = s[l], wi = w[i];
+                    s[l] = c * sl + sgl * wi;
+                    w[i] = (i == j) ? tau : (-sgl * sl + c * wi);
+                }
             }
-            for (int i = j + tid; i < n; i += G) {
-                const int l = jj + (i - j);
-                const double sl = s[l], wi = w[i];
-                s[l] = c * sl + sgl * wi;
-                w[i] = (i == j) ? tau : (-sgl * sl + c * wi);
-            }
+            __syncwarp();
         }
-        gsync<G>();
+        if (lane == 0) s[rowstart(n, n - 1)] = w[n - 1];
     }
-    if (tid == 0) s[rowstart(n - 1)] = w[n - 1];
     gsync<G>();
 }
 
@@ -595,235 +656,320 @@ __device__ void r1coef_g(int n, const double *v, const double *w, double *scr) {
     gsync<G>();
 }
 
-// r1mpyq: apply the recorded rotations to A (m x n, column-major, lda) -- one thread per row
+// r1mpyq: apply the recorded rotations to A (m x n, column-major, lda): one thread per row, the
+// row streamed through registers in chunks of 8 columns so that the loads overlap the chain.
 template <int G>
 __device__ void r1mpyq_g(int m, int n, double *a, int lda, const double *scr) {
     const int tid = threadIdx.x % G;
     const double *c1 = scr, *s1 = scr + n, *c2 = scr + 2 * n, *s2 = scr + 3 * n;
+    constexpr int CH = 8;
     gsync<G>();
     for (int i = tid; i < m; i += G) {
-        double an = a[i + (size_t)(n - 1) * lda];
-        for (int j = n - 2; j >= 0; --j) {
-            const double aj = a[i + (size_t)j * lda];
-            a[i + (size_t)j * lda] = c1[j] * aj - s1[j] * an;
-            an = s1[j] * aj + c1[j] * an;
+        double *row = a + i;
+        double an = row[(size_t)(n - 1) * lda];
+        double buf[CH];
+        for (int j0 = n - 2; j0 >= 0; j0 -= CH) {             // first set: j = n-2 .. 0
+#pragma unroll
+            for (int k = 0; k < CH; ++k) if (j0 - k >= 0) buf[k] = row[(size_t)(j0 - k) * lda];
+#pragma unroll
+            for (int k = 0; k < CH; ++k) if (j0 - k >= 0) {
+                const int j = j0 - k;
+                const double aj = buf[k];
+                buf[k] = c1[j] * aj - s1[j] * an;
+                an = s1[j] * aj + c1[j] * an;
+            }
+#pragma unroll
+            for (int k = 0; k < CH; ++k) if (j0 - k >= 0) row[(size_t)(j0 - k) * lda] = buf[k];
         }
-        for (int j = 0; j < n - 1; ++j) {
-            const double aj = a[i + (size_t)j * lda];
-            a[i + (size_t)j * lda] = c2[j] * aj + s2[j] * an;
-            an = -s2[j] * aj + c2[j] * an;
+        for (int j0 = 0; j0 < n - 1; j0 += CH) {               // second set: j = 0 .. n-2
+#pragma unroll
+            for (int k = 0; k < CH; ++k) if (j0 + k < n - 1) buf[k] = row[(size_t)(j0 + k) * lda];
+#pragma unroll
+            for (int k = 0; k < CH; ++k) if (j0 + k < n - 1) {
+                const int j = j0 + k;
+                const double aj = buf[k];
+                buf[k] = c2[j] * aj + s2[j] * an;
+                an = -s2[j] * aj + c2[j] * an;
+            }
+#pragma unroll
+            for (int k = 0; k < CH; ++k) if (j0 + k < n - 1) row[(size_t)(j0 + k) * lda] = buf[k];
         }
-        a[i + (size_t)(n - 1) * lda] = an;
+        row[(size_t)(n - 1) * lda] = an;
     }
     gsync<G>();
 }
 
-// ---- kernel 2: advance every problem that received its function values -------------------------
-template <int MODEL, int G>
-__global__ void __launch_bounds__((G == 32) ? 128 : G)
-advance(SolverDev D, int cur) {
-    constexpr int GROUPS = (G == 32) ? 4 : 1;
-    __shared__ double red_all[GROUPS][8];
+// ---- shared state of one problem inside the Powell-hybrid kernels ------------------------------
+struct Work {
+    double *x, *xe, *fvec, *diag, *qtf, *wa1, *wa2, *wa3, *wa4, *scr, *r, *q;
+    int ldq;
+};
+
+// dogleg step from the current factors, trial point xe = x + p, and the request for F(xe)
+template <int G>
+__device__ void dogleg_and_request(const SolverDev &D, long b, const Work &W, int *is, double *ds, double *red,
+                                   int *next_res, int *next_cnt) {
+    const int n = D.P, tid = threadIdx.x % G;
+    const double delta = ds[D_DELTA];
+    dogleg_g<G>(n, W.r, W.diag, W.qtf, delta, W.wa1, W.wa2, W.wa3, red);
+    for (int j = tid; j < n; j += G) {
+        const double pj = -W.wa1[j];
+        W.wa1[j] = pj;
+        W.xe[j] = W.x[j] + pj;            // trial point (MINPACK's wa2)
+        W.wa3[j] = W.diag[j] * pj;
+    }
+    gsync<G>();
+    const double pnorm = enorm_g<G>(n, W.wa3, red);
+    gsync<G>();
+    if (tid == 0) {
+        ds[D_PNORM] = pnorm;
+        if (is[I_ITER] == 1) ds[D_DELTA] = fmin(delta, pnorm);
+        is[I_PHASE] = PH_TRIAL;
+        next_res[atomicAdd(&next_cnt[0], 1)] = (int)b;
+    }
+}
+
+// shared-memory carve for one group: [13 P vectors][R][Q]
+template <int G>
+SOCP_DEV double *group_smem(const SolverDev &D, int per_group_doubles) {
+    extern __shared__ double smem_all[];
+    const int grp = (G == 32) ? (threadIdx.x >> 5) : 0;
+    return smem_all + (size_t)grp * per_group_doubles;
+}
+
+// ---- kernel 2b: problems whose residual arrived (first evaluation or trial point) ---------------
+template <int G, bool STAGE_R>
+__global__ void __launch_bounds__(128, 4)
+hybrd_res_kernel(SolverDev D, int cur, int per_group_doubles) {
+    const int GROUPS = (G == 32) ? (int)(blockDim.x >> 5) : 1;
     const int grp = (G == 32) ? (threadIdx.x >> 5) : 0;
     const int tid = threadIdx.x % G;
-    double *red = red_all[grp];
-    const int nres = D.counts[cur * 2 + 0], njac = D.counts[cur * 2 + 1];
+    const int n = D.P;
+    double *sm = group_smem<G>(D, per_group_doubles);
+    double *red = sm;                                    // 8 doubles
+    double *vec = sm + 8;
+    const int nres = D.counts[cur * 2 + 0];
     const int *res_list = D.lists + (size_t)(cur * 2 + 0) * D.B;
-    const int *jac_list = D.lists + (size_t)(cur * 2 + 1) * D.B;
     int *next_res = D.lists + (size_t)((1 - cur) * 2 + 0) * D.B;
     int *next_jac = D.lists + (size_t)((1 - cur) * 2 + 1) * D.B;
     int *next_cnt = D.counts + (1 - cur) * 2;
-    const int n = D.P;
     const double p1 = .1, p5 = .5, p001 = .001, p0001 = 1e-4;
 
-    for (long g = (long)blockIdx.x * GROUPS + grp; g < (long)nres + njac; g += (long)gridDim.x * GROUPS) {
-        const long b = (g < nres) ? res_list[g] : jac_list[g - nres];
+    for (long g = (long)blockIdx.x * GROUPS + grp; g < nres; g += (long)gridDim.x * GROUPS) {
+        const long b = res_list[g];
         int *is = D.istate + b * I_COUNT;
         double *ds = D.dstate + b * D_COUNT;
-        double *x = D.x + b * n, *xe = D.xe + b * n, *fvec = D.fvec + b * n, *diag = D.diag + b * n;
-        double *qtf = D.qtf + b * n, *wa1 = D.wa1 + b * n, *wa2 = D.wa2 + b * n, *wa3 = D.wa3 + b * n, *wa4 = D.wa4 + b * n;
-        double *fjac = D.fjac + (size_t)b * n * n, *r = D.r + (size_t)b * D.LR, *scr = D.scr + (size_t)b * 4 * n;
-        const double *jends_b = D.jends + (size_t)b * D.nJ * D.REC;
         gsync<G>();
-        int phase = is[I_PHASE];
-        bool need_dogleg = false;
-
+        const int phase = is[I_PHASE];
         if (phase == PH_F0) {
-            // first residual: fvec = F(x)
-            const int trial = 1 - is[I_BASE];
-            const double *te = D.ends + ((b * 2 + trial) * D.M) * D.REC;
-            if (tid == 0) assemble<MODEL>(D, b, -1, 0.0, te, jends_b, fvec);
-            gsync<G>();
-            const double fnorm = enorm_g<G>(n, fvec, red);
+            // first residual: fvec = F(x) was written by assemble_kernel
+            const double fnorm = enorm_g<G>(n, D.fvec + b * n, red);
             gsync<G>();
             if (tid == 0) {
-                is[I_BASE] = trial;
+                is[I_BASE] = 1 - is[I_BASE];
                 is[I_NFEV] = 1;
                 ds[D_FNORM] = fnorm;
                 is[I_ITER] = 1; is[I_NCSUC] = 0; is[I_NCFAIL] = 0; is[I_NSLOW1] = 0; is[I_NSLOW2] = 0;
-            }
-            if (D.run_mode == RUN_RESIDUAL) {
-                if (tid == 0) is[I_PHASE] = PH_IDLE;
-            } else {
-                if (tid == 0) {
+                if (D.run_mode == RUN_RESIDUAL) is[I_PHASE] = PH_IDLE;
+                else {
                     is[I_PHASE] = PH_JAC;
                     next_jac[atomicAdd(&next_cnt[1], 1)] = (int)b;
                 }
             }
-        } else if (phase == PH_JAC) {
-            // forward-difference Jacobian from the perturbed segments (fdjac1, dense)
-            const double *be = D.ends + ((b * 2 + is[I_BASE]) * D.M) * D.REC;
-            for (int j = tid; j < n; j += G) {
-                const double h = fd_step(xe[j], D.epsfcn);
-                double *colj = fjac + (size_t)j * n;
-                assemble<MODEL>(D, b, j, h, be, jends_b, colj);
-                for (int i = 0; i < n; ++i) colj[i] = (colj[i] - fvec[i]) / h;
-            }
-            gsync<G>();
-            if (D.run_mode == RUN_FDJAC) {
-                if (tid == 0) is[I_PHASE] = PH_IDLE;
-            } else {
-                if (tid == 0) { is[I_NFEV] += n; is[I_JEVAL] = 1; }
-                for (int i = tid; i < n; i += G) qtf[i] = fvec[i];
-                // wa1 = rdiag, wa2 = acnorm
-                qrfac_g<G>(n, fjac, wa1, wa2, qtf, red);
-                const int iter = is[I_ITER];
-                if (iter == 1) {
-                    for (int j = tid; j < n; j += G) {
-                        double dj = wa2[j];
-                        if (dj == 0.) dj = 1.;
-                        diag[j] = dj;
-                        wa3[j] = dj * x[j];
-                    }
-                    gsync<G>();
-                    const double xnorm = enorm_g<G>(n, wa3, red);
-                    double delta = D.factor * xnorm;
-                    if (delta == 0.) delta = D.factor;
-                    gsync<G>();
-                    if (tid == 0) { ds[D_XNORM] = xnorm; ds[D_DELTA] = delta; }
-                }
-                pack_r_g<G>(n, fjac, wa1, r);
-                qform_g<G>(n, fjac, wa1);
-                for (int j = tid; j < n; j += G) diag[j] = fmax(diag[j], wa2[j]);
-                gsync<G>();
-                need_dogleg = true;
-            }
-        } else if (phase == PH_TRIAL) {
-            // wa4 = F(x + p)
-            const int trial = 1 - is[I_BASE];
-            const double *te = D.ends + ((b * 2 + trial) * D.M) * D.REC;
-            if (tid == 0) assemble<MODEL>(D, b, -1, 0.0, te, jends_b, wa4);
-            gsync<G>();
-            const double fnorm1 = enorm_g<G>(n, wa4, red);
-            double fnorm = ds[D_FNORM], delta = ds[D_DELTA], xnorm = ds[D_XNORM];
-            const double pnorm = ds[D_PNORM];
-            int iter = is[I_ITER], ncsuc = is[I_NCSUC], ncfail = is[I_NCFAIL], nslow1 = is[I_NSLOW1], nslow2 = is[I_NSLOW2];
-            const int jeval = is[I_JEVAL];
-            const int nfev = is[I_NFEV] + 1;
-            double actred = -1.;
-            if (fnorm1 < fnorm) { const double q = fnorm1 / fnorm; actred = 1. - q * q; }
-            // predicted reduction: wa3 = qtf + R * wa1
-            gsync<G>();
-            for (int i = tid; i < n; i += G) {
-                const int jj = i * n - (i * (i - 1)) / 2;
-                double sum = 0.;
-                for (int j = i; j < n; ++j) sum += r[jj + (j - i)] * wa1[j];
-                wa3[i] = qtf[i] + sum;
-            }
-            gsync<G>();
-            const double temp = enorm_g<G>(n, wa3, red);
-            double prered = 0.;
-            if (temp < fnorm) { const double q = temp / fnorm; prered = 1. - q * q; }
-            double ratio = 0.;
-            if (prered > 0.) ratio = actred / prered;
-            if (ratio < p1) {
-                ncsuc = 0; ++ncfail; delta = p5 * delta;
-            } else {
-                ncfail = 0; ++ncsuc;
-                if (ratio >= p5 || ncsuc > 1) delta = fmax(delta, pnorm / p5);
-                if (fabs(ratio - 1.) <= p1) delta = pnorm / p5;
-            }
-            int base = is[I_BASE];
-            gsync<G>();
-            if (ratio >= p0001) {
-                // successful iteration: x <- x + p, fvec <- wa4
-                for (int j = tid; j < n; j += G) {
-                    const double xj = xe[j];
-                    x[j] = xj;
-                    wa2[j] = diag[j] * xj;
-                    fvec[j] = wa4[j];
-                }
-                gsync<G>();
-                xnorm = enorm_g<G>(n, wa2, red);
-                fnorm = fnorm1;
-                ++iter;
-                base = trial;
-            }
-            ++nslow1;
-            if (actred >= p001) nslow1 = 0;
-            if (jeval) ++nslow2;
-            if (actred >= p1) nslow2 = 0;
-            int info = 0;
-            if (delta <= D.xtol * xnorm || fnorm == 0.) info = 1;
-            if (info == 0) {
-                if (nfev >= D.maxfev) info = 2;
-                if (p1 * fmax(p1 * delta, pnorm) <= EPSMCH * xnorm) info = 3;
-                if (nslow2 == 5) info = 4;
-                if (nslow1 == 10) info = 5;
-            }
-            gsync<G>();
-            if (tid == 0) {
-                is[I_ITER] = iter; is[I_NCSUC] = ncsuc; is[I_NCFAIL] = ncfail; is[I_NSLOW1] = nslow1; is[I_NSLOW2] = nslow2;
-                is[I_NFEV] = nfev; is[I_BASE] = base;
-                ds[D_FNORM] = fnorm; ds[D_DELTA] = delta; ds[D_XNORM] = xnorm;
-            }
-            if (info != 0) {
-                if (tid == 0) { is[I_INFO] = info; is[I_PHASE] = PH_IDLE; }      // retire
-            } else if (ncfail == 2) {
-                // re-evaluate the Jacobian at x
-                for (int j = tid; j < n; j += G) xe[j] = x[j];
-                if (tid == 0) {
-                    is[I_PHASE] = PH_JAC;
-                    next_jac[atomicAdd(&next_cnt[1], 1)] = (int)b;
-                }
-            } else {
-                // rank-one (Broyden) update of the QR factors
-                for (int j = tid; j < n; j += G) {
-                    const double *cj = fjac + (size_t)j * n;
-                    double sum = 0.;
-                    for (int i = 0; i < n; ++i) sum += cj[i] * wa4[i];
-                    wa2[j] = (sum - wa3[j]) / pnorm;
-                    wa1[j] = diag[j] * ((diag[j] * wa1[j]) / pnorm);
-                    if (ratio >= p0001) qtf[j] = sum;
-                }
-                r1updt_g<G>(n, r, wa1, wa2, wa3, scr, scr + n);
-                r1coef_g<G>(n, wa2, wa3, scr);
-                r1mpyq_g<G>(n, n, fjac, n, scr);
-                r1mpyq_g<G>(1, n, qtf, 1, scr);
-                if (tid == 0) is[I_JEVAL] = 0;
-                need_dogleg = true;
-            }
+            continue;
         }
+        // ---- trial point evaluated: wa4 = F(x + p) ----
+        Work W;
+        W.x = vec; W.xe = vec + n; W.fvec = vec + 2 * n; W.diag = vec + 3 * n; W.qtf = vec + 4 * n;
+        W.wa1 = vec + 5 * n; W.wa4 = vec + 6 * n; W.wa2 = vec + 7 * n; W.wa3 = vec + 8 * n; W.scr = vec + 9 * n;
+        W.r = STAGE_R ? vec + 13 * n : D.r + (size_t)b * D.LR;
+        W.q = D.fjac + (size_t)b * n * n;
+        W.ldq = n;
+        gcopy<G>(W.x, D.x + b * n, n); gcopy<G>(W.xe, D.xe + b * n, n); gcopy<G>(W.fvec, D.fvec + b * n, n);
+        gcopy<G>(W.diag, D.diag + b * n, n); gcopy<G>(W.qtf, D.qtf + b * n, n); gcopy<G>(W.wa1, D.wa1 + b * n, n);
+        gcopy<G>(W.wa4, D.wa4 + b * n, n);
+        if (STAGE_R) gcopy<G>(W.r, D.r + (size_t)b * D.LR, D.LR);
+        gsync<G>();
 
-        if (need_dogleg) {
-            const double delta = ds[D_DELTA];
-            dogleg_g<G>(n, r, diag, qtf, delta, wa1, wa2, wa3, red);
-            for (int j = tid; j < n; j += G) {
-                const double pj = -wa1[j];
-                wa1[j] = pj;
-                xe[j] = x[j] + pj;            // trial point (MINPACK's wa2)
-                wa3[j] = diag[j] * pj;
-            }
-            gsync<G>();
-            const double pnorm = enorm_g<G>(n, wa3, red);
-            gsync<G>();
-            if (tid == 0) {
-                ds[D_PNORM] = pnorm;
-                if (is[I_ITER] == 1) ds[D_DELTA] = fmin(delta, pnorm);
-                is[I_PHASE] = PH_TRIAL;
-                next_res[atomicAdd(&next_cnt[0], 1)] = (int)b;
-            }
+        const double fnorm1 = enorm_g<G>(n, W.wa4, red);
+        double fnorm = ds[D_FNORM], delta = ds[D_DELTA], xnorm = ds[D_XNORM];
+        const double pnorm = ds[D_PNORM];
+        int iter = is[I_ITER], ncsuc = is[I_NCSUC], ncfail = is[I_NCFAIL], nslow1 = is[I_NSLOW1], nslow2 = is[I_NSLOW2];
+        const int jeval = is[I_JEVAL];
+        const int nfev = is[I_NFEV] + 1;
+        const int trial = 1 - is[I_BASE];
+        double actred = -1.;
+        if (fnorm1 < fnorm) { const double q = fnorm1 / fnorm; actred = 1. - q * q; }
+        // predicted reduction: wa3 = qtf + R * wa1
+        rmulv_g<G>(n, W.r, W.wa1, W.qtf, W.wa3);
+        const double temp = enorm_g<G>(n, W.wa3, red);
+        double prered = 0.;
+        if (temp < fnorm) { const double q = temp / fnorm; prered = 1. - q * q; }
+        double ratio = 0.;
+        if (prered > 0.) ratio = actred / prered;
+        if (ratio < p1) {
+            ncsuc = 0; ++ncfail; delta = p5 * delta;
+        } else {
+            ncfail = 0; ++ncsuc;
+            if (ratio >= p5 || ncsuc > 1) delta = fmax(delta, pnorm / p5);
+            if (fabs(ratio - 1.) <= p1) delta = pnorm / p5;
         }
+        int base = is[I_BASE];
+        gsync<G>();
+        if (ratio >= p0001) {
+            // successful iteration: x <- x + p, fvec <- wa4
+            for (int j = tid; j < n; j += G) {
+                const double xj = W.xe[j];
+                W.x[j] = xj;
+                W.wa2[j] = W.diag[j] * xj;
+                W.fvec[j] = W.wa4[j];
+            }
+            gsync<G>();
+            xnorm = enorm_g<G>(n, W.wa2, red);
+            fnorm = fnorm1;
+            ++iter;
+            base = trial;
+        }
+        ++nslow1;
+        if (actred >= p001) nslow1 = 0;
+        if (jeval) ++nslow2;
+        if (actred >= p1) nslow2 = 0;
+        int info = 0;
+        if (delta <= D.xtol * xnorm || fnorm == 0.) info = 1;
+        if (info == 0) {
+            if (nfev >= D.maxfev) info = 2;
+            if (p1 * fmax(p1 * delta, pnorm) <= EPSMCH * xnorm) info = 3;
+            if (nslow2 == 5) info = 4;
+            if (nslow1 == 10) info = 5;
+        }
+        gsync<G>();
+        if (tid == 0) {
+            is[I_ITER] = iter; is[I_NCSUC] = ncsuc; is[I_NCFAIL] = ncfail; is[I_NSLOW1] = nslow1; is[I_NSLOW2] = nslow2;
+            is[I_NFEV] = nfev; is[I_BASE] = base;
+            ds[D_FNORM] = fnorm; ds[D_DELTA] = delta; ds[D_XNORM] = xnorm;
+        }
+        bool store_r = false;
+        if (info != 0) {
+            if (tid == 0) { is[I_INFO] = info; is[I_PHASE] = PH_IDLE; }      // retire (convergence mask)
+        } else if (ncfail == 2) {
+            // re-evaluate the Jacobian at x
+            for (int j = tid; j < n; j += G) W.xe[j] = W.x[j];
+            if (tid == 0) {
+                is[I_PHASE] = PH_JAC;
+                next_jac[atomicAdd(&next_cnt[1], 1)] = (int)b;
+            }
+        } else {
+            // rank-one (Broyden) update of the QR factors: sum_j = Q(:,j) . wa4, one warp per
+            // column, four columns in flight so that the HBM/L2 loads of Q overlap
+            {
+                const int lane = threadIdx.x & 31, warp = tid >> 5;
+                constexpr int NW = G / 32;
+                for (int j0 = warp * 4; j0 < n; j0 += NW * 4) {
+                    double part[4] = {0., 0., 0., 0.};
+                    for (int i = lane; i < n; i += 32) {
+                        const double wi = W.wa4[i];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            if (j0 + k < n) part[k] += W.q[(size_t)(j0 + k) * W.ldq + i] * wi;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int j = j0 + k;
+                        if (j < n) {
+                            const double sum = warp_sum(part[k]);
+                            if (lane == 0) {
+                                W.wa2[j] = (sum - W.wa3[j]) / pnorm;
+                                W.wa1[j] = W.diag[j] * ((W.diag[j] * W.wa1[j]) / pnorm);
+                                if (ratio >= p0001) W.qtf[j] = sum;
+                            }
+                        }
+                    }
+                }
+            }
+            r1updt_g<G>(n, W.r, W.wa1, W.wa2, W.wa3, W.scr, W.scr + n);
+            r1coef_g<G>(n, W.wa2, W.wa3, W.scr);
+            r1mpyq_g<G>(n, n, W.q, W.ldq, W.scr);
+            r1mpyq_g<G>(1, n, W.qtf, 1, W.scr);
+            if (tid == 0) is[I_JEVAL] = 0;
+            dogleg_and_request<G>(D, b, W, is, ds, red, next_res, next_cnt);
+            store_r = true;
+        }
+        gsync<G>();
+        gcopy<G>(D.x + b * n, W.x, n); gcopy<G>(D.xe + b * n, W.xe, n); gcopy<G>(D.fvec + b * n, W.fvec, n);
+        gcopy<G>(D.qtf + b * n, W.qtf, n); gcopy<G>(D.wa1 + b * n, W.wa1, n);
+        if (STAGE_R && store_r) gcopy<G>(D.r + (size_t)b * D.LR, W.r, D.LR);
+        gsync<G>();
+    }
+}
+
+// ---- kernel 2c: problems whose forward-difference Jacobian arrived ------------------------------
+template <int G, bool STAGE_R, bool STAGE_Q>
+__global__ void __launch_bounds__(128)
+hybrd_jac_kernel(SolverDev D, int cur, int per_group_doubles) {
+    const int GROUPS = (G == 32) ? (int)(blockDim.x >> 5) : 1;
+    const int grp = (G == 32) ? (threadIdx.x >> 5) : 0;
+    const int tid = threadIdx.x % G;
+    const int n = D.P;
+    double *sm = group_smem<G>(D, per_group_doubles);
+    double *red = sm;
+    double *vec = sm + 8;
+    const int njac = D.counts[cur * 2 + 1];
+    const int *jac_list = D.lists + (size_t)(cur * 2 + 1) * D.B;
+    int *next_res = D.lists + (size_t)((1 - cur) * 2 + 0) * D.B;
+    int *next_cnt = D.counts + (1 - cur) * 2;
+    const int ldq_s = n | 1;                               // odd leading dimension in shared memory
+
+    for (long g = (long)blockIdx.x * GROUPS + grp; g < njac; g += (long)gridDim.x * GROUPS) {
+        const long b = jac_list[g];
+        int *is = D.istate + b * I_COUNT;
+        double *ds = D.dstate + b * D_COUNT;
+        gsync<G>();
+        if (D.run_mode == RUN_FDJAC) {                     // the Jacobian itself was the request
+            if (tid == 0) is[I_PHASE] = PH_IDLE;
+            continue;
+        }
+        Work W;
+        W.x = vec; W.xe = vec + n; W.fvec = vec + 2 * n; W.diag = vec + 3 * n; W.qtf = vec + 4 * n;
+        W.wa1 = vec + 5 * n; W.wa4 = vec + 6 * n; W.wa2 = vec + 7 * n; W.wa3 = vec + 8 * n; W.scr = vec + 9 * n;
+        double *after = vec + 13 * n;
+        W.r = STAGE_R ? after : D.r + (size_t)b * D.LR;
+        if (STAGE_R) after += D.LR;
+        double *gq = D.fjac + (size_t)b * n * n;
+        W.q = STAGE_Q ? after : gq;
+        W.ldq = STAGE_Q ? ldq_s : n;
+        gcopy<G>(W.x, D.x + b * n, n); gcopy<G>(W.fvec, D.fvec + b * n, n); gcopy<G>(W.diag, D.diag + b * n, n);
+        if (STAGE_Q)
+            for (int e = tid; e < n * n; e += G) W.q[(e % n) + (size_t)(e / n) * ldq_s] = gq[e];
+        gsync<G>();
+        if (tid == 0) { is[I_NFEV] += n; is[I_JEVAL] = 1; }
+        for (int i = tid; i < n; i += G) W.qtf[i] = W.fvec[i];
+        // wa1 = rdiag, wa2 = acnorm
+        qrfac_g<G>(n, W.q, W.ldq, W.wa1, W.wa2, W.qtf, red);
+        if (is[I_ITER] == 1) {
+            for (int j = tid; j < n; j += G) {
+                double dj = W.wa2[j];
+                if (dj == 0.) dj = 1.;
+                W.diag[j] = dj;
+                W.wa3[j] = dj * W.x[j];
+            }
+            gsync<G>();
+            const double xnorm = enorm_g<G>(n, W.wa3, red);
+            double delta = D.factor * xnorm;
+            if (delta == 0.) delta = D.factor;
+            gsync<G>();
+            if (tid == 0) { ds[D_XNORM] = xnorm; ds[D_DELTA] = delta; }
+        }
+        pack_r_g<G>(n, W.q, W.ldq, W.wa1, W.r);
+        qform_g<G>(n, W.q, W.ldq, W.wa1);
+        for (int j = tid; j < n; j += G) W.diag[j] = fmax(W.diag[j], W.wa2[j]);
+        gsync<G>();
+        dogleg_and_request<G>(D, b, W, is, ds, red, next_res, next_cnt);
+        gsync<G>();
+        gcopy<G>(D.xe + b * n, W.xe, n); gcopy<G>(D.diag + b * n, W.diag, n);
+        gcopy<G>(D.qtf + b * n, W.qtf, n); gcopy<G>(D.wa1 + b * n, W.wa1, n);
+        if (STAGE_R) gcopy<G>(D.r + (size_t)b * D.LR, W.r, D.LR);
+        if (STAGE_Q)
+            for (int e = tid; e < n * n; e += G) gq[e] = W.q[(e % n) + (size_t)(e / n) * ldq_s];
         gsync<G>();
     }
 }

@@ -72,7 +72,14 @@ def test_fdjac_vs_oracle(oracle_lib, name):
     for seed in (1, 2, 3):
         dev = np.maximum(dev, np.abs(ora.fdjac(spec, noise_ulps=8.0, seed=seed) - want))
     colmax = np.max(np.abs(want), axis=0)
-    tol = 4 * dev + 1e-9 * colmax[None, :]
+    # a forward difference is quantised: F changes in steps of one ulp of its operands (the node
+    # states, |x| ~ scale), so entries move in steps of ulp(scale) / h_j whatever the probe says
+    x0 = np.array(spec["x0"])
+    h = np.sqrt(1e-15) * np.abs(x0)
+    h[h == 0] = np.sqrt(1e-15)
+    scale = max(np.max(np.abs(x0)), np.max(np.abs(ora.residual(spec))), 1.0)
+    quantum = 2.220446049250313e-16 * scale / h
+    tol = 4 * dev + 8 * quantum[None, :] + 1e-9 * colmax[None, :]
     bad = np.abs(got - want) > tol
     assert not np.any(bad), "%s: %d FD-Jacobian entries differ beyond rounding amplification (worst %.3e)" % (
         name, bad.sum(), np.max(np.abs(got - want)[bad] / tol[bad]))
