@@ -211,6 +211,7 @@ def main():
     import torch
     import torch.distributed as dist
     import socp_b200 as sb
+    from socp_b200 import sharding
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (the engine has no CPU fallback)")
     torch.cuda.set_device(local)
@@ -236,7 +237,6 @@ def main():
     d_info = torch.empty(B, dtype=torch.int32, device=dev)
     d_nfev = torch.empty(B, dtype=torch.int32, device=dev)
     d_fnorm = torch.empty(B, dtype=torch.float64, device=dev)
-    gathered = torch.empty((world, B, P + 2), dtype=torch.float64, device=dev) if world > 1 else None
     eng.use_torch_stream()
 
     def step():
@@ -244,8 +244,7 @@ def main():
         eng.solve_batch(shape, d_mp, d_time, d_Xb, d_x, xtol=1e-6, maxfev=10000, info=d_info, nfev=d_nfev, fnorm=d_fnorm)
         if world > 1:
             # the only exchange of the path: gather converged unknowns + status over NVLink
-            pack = torch.cat([d_x, d_info.double()[:, None], d_nfev.double()[:, None]], dim=1)
-            dist.all_gather_into_tensor(gathered.view(world * B, P + 2), pack)
+            sharding.gather_results(d_x, d_info, d_nfev)
 
     for _ in range(args.warmup):
         step()

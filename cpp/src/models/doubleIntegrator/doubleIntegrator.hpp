@@ -1,0 +1,35 @@
+// cpp/src/models/doubleIntegrator/doubleIntegrator.hpp -- mirror of
+// src/models/doubleIntegrator/doubleIntegrator.hpp:16-79.  modelOrder is accepted as in the
+// reference; this engine always solves with the forward-difference Powell hybrid (hybrd), the
+// analytic-Jacobian path (hybrj, modelOrder == 1) is not built yet.
+#include "../../socp/model.hpp"
+
+#include <iostream>
+
+#ifndef _DOUBLEINTEGRATOR_H_
+#define _DOUBLEINTEGRATOR_H_
+
+class doubleIntegrator : public model
+{
+public:
+	struct parameters_struct{
+		real u_max;				// max normalized control
+		real a_max;				// max acceleration
+		real muT;				// weight for time cost
+	};
+
+	doubleIntegrator(int modelOrder, std::string the_fileTrace);
+	virtual ~doubleIntegrator();
+
+	parameters_struct & GetParameterData();
+	void SetStepNumber(int step);		///< writes an unused field in the reference (doubleIntegrator.cpp:313): 30 steps stay
+
+	virtual int DeviceModelId() const;
+	virtual std::vector<real> DeviceParams() const;
+
+private:
+	struct data_struct;
+	data_struct *data;
+};
+
+#endif //_DOUBLEINTEGRATOR_H_
