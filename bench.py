@@ -123,6 +123,16 @@ class CpuPool:
 
 
 # ---------------------------------------------------------------------------------------------
+def hbm_peak_gbs():
+    """Measured copy bandwidth of this pool's B200s (driver-written MEASURED_PEAKS.json), else the
+    fallback stated in B200_PROFILING.md."""
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+    except Exception:
+        return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md; MEASURED_PEAKS.json absent)"
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -284,18 +294,41 @@ def main():
     rk4_steps_per_step = float(agg[0].item()) / args.steps
     rk4_rate = rk4_steps_per_step / (ms_per_step * 1e-3)
 
-    # roofline of the RK4 integration kernel: nominal flops of the steps it executed / its own time
+    # rooflines, per kernel of the solver round (CUDA events around every launch on the engine stream)
     flops = FLOPS_PER_RK4_STEP["goddard"]
+    peak_tf = peak_gflops / 1e3
+    hbm_peak, hbm_src = hbm_peak_gbs()
     int_ms, int_n = st["integrate_ms"], max(st["integrate_launches"], 1.0)
-    adv_ms = st["advance_ms"]
-    achieved_tf = (st["rk4_steps"] * flops) / (int_ms * 1e-3) / 1e12 if int_ms > 0 else 0.0
-    roofline = {"kernel": "integrate_worklist<goddard>", "bound": "fp64", "achieved": achieved_tf,
-                "peak": peak_gflops / 1e3, "unit": "TFLOP/s", "frac": achieved_tf / (peak_gflops / 1e3),
-                "peak_source": "measured on this GPU: register-resident DFMA chain (socp_measure_fp64_peak); "
-                               "MEASURED_PEAKS.json has no FP64 entry",
-                "traffic": None, "avg_launch_ms": int_ms / int_n, "launches": int_n,
-                "flops_per_rk4_step": flops, "share_of_step": int_ms / ms if ms > 0 else None,
-                "advance_kernel_share_of_step": adv_ms / ms if ms > 0 else None}
+    jac_ms, res_ms, asm_ms = st["jac_ms"], st["advance_ms"] - st["jac_ms"], st["assemble_ms"]
+    LR = P * (P + 1) // 2
+    # hybrd_res_kernel, per Broyden iteration of one problem: Q read + written once (2 P^2), packed R
+    # read + written once (2 LR), seven work vectors in and five out (12 P)   [DESIGN.md section 5]
+    bytes_iter = 8.0 * (2 * P * P + 2 * LR + 12 * P)
+    # hybrd_jac_kernel, per factorisation: Householder QR (4/3 P^3) + accumulation of Q (4/3 P^3)
+    flops_jac = 8.0 / 3.0 * P ** 3
+    kern = {
+        "integrate_worklist<goddard>": {"bound": "fp64", "ms": int_ms, "unit": "TFLOP/s", "peak": peak_tf,
+                                        "achieved": st["rk4_steps"] * flops / (int_ms * 1e-3) / 1e12 if int_ms > 0 else 0.0},
+        "hybrd_res_kernel": {"bound": "hbm", "ms": res_ms, "unit": "GB/s", "peak": hbm_peak,
+                             "achieved": st["iterations"] * bytes_iter / (res_ms * 1e-3) / 1e9 if res_ms > 0 else 0.0},
+        "hybrd_jac_kernel": {"bound": "fp64", "ms": jac_ms, "unit": "TFLOP/s", "peak": peak_tf,
+                             "achieved": st["jac_evals"] * flops_jac / (jac_ms * 1e-3) / 1e12 if jac_ms > 0 else 0.0},
+        "assemble_kernel<goddard>": {"bound": "latency", "ms": asm_ms, "unit": None, "peak": None, "achieved": None},
+    }
+    for k in kern.values():
+        k["share_of_step"] = k["ms"] / ms if ms > 0 else None
+        k["frac"] = (k["achieved"] / k["peak"]) if k["peak"] else None
+    dom = max((k for k in kern if kern[k]["peak"]), key=lambda k: kern[k]["ms"])
+    d = kern[dom]
+    n_launch = max(st["solver_rounds"], 1.0)
+    roofline = {"kernel": dom, "bound": d["bound"], "achieved": d["achieved"], "peak": d["peak"], "unit": d["unit"],
+                "frac": d["frac"], "traffic": None, "avg_launch_ms": d["ms"] / n_launch, "launches": n_launch,
+                "share_of_step": d["share_of_step"],
+                "algorithmic_bytes_per_problem_iteration": bytes_iter,
+                "problem_iterations": st["iterations"], "jacobian_factorisations": st["jac_evals"],
+                "peak_source": {"hbm": hbm_src, "fp64": "measured on this GPU: register-resident DFMA chain "
+                                "(socp_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 entry"},
+                "flops_per_rk4_step": flops, "kernels": kern}
 
     # end to end through the public API with pinned host buffers
     e2e = None

@@ -11,10 +11,10 @@ class obstacle:public map
 {
 public:
 	struct parameters_struct{
-		real phiObs;          	///< weight of obstacle function
-		real psiWP;          	///< weight of waypoint function
-		real muObs;  			///< parameter for penalization dispersion
-		real sigmaWP;			///< parameter for penalization dispersion
+		real phiObs;
+		real psiWP;
+		real muObs;
+		real sigmaWP;
 	};
 
 	obstacle(std::string the_fileObstacles = std::string(""), std::string the_fileWP = std::string(""));

@@ -11,14 +11,14 @@ class covid19:public model
 {
 public:
 	struct parameters_struct{
-		real R0;					///< the number of secondary infections each infected individual produces
-		real Tinf;					///< duration patient is infectious
-		real Tinc;					///< incubation period
-		real N;						///< size of population
-		real Imax;					///< maximum Infectious permitted
-		real muI;					///< penalization coefficient to constrain Infectious
-		real umin;					///< minimum control
-		real umax;					///< maximum control
+		real R0;
+		real Tinf;
+		real Tinc;
+		real N;
+		real Imax;
+		real muI;
+		real umin;
+		real umax;
 	};
 
 	covid19(std::string the_fileTrace = std::string(""));

@@ -13,9 +13,9 @@ class doubleIntegrator : public model
 {
 public:
 	struct parameters_struct{
-		real u_max;				// max normalized control
-		real a_max;				// max acceleration
-		real muT;				// weight for time cost
+		real u_max;
+		real a_max;
+		real muT;
 	};
 
 	doubleIntegrator(int modelOrder, std::string the_fileTrace);

@@ -13,14 +13,14 @@ class goddard:public model
 {
 public:
 	struct parameters_struct{
-		real C = 3.5;					///< coefficient for thrust
-		real b = 7.0;					///< coefficient for mass flow rate
-		real KD = 310.0;				///< coefficient for drag
-		real kr = 500.0;				///< coefficient for density of air
-		real u_max = 1.0;				///< max normalized control
-		real mu1 = 1.0;					///< weight for the cost on the norm of the control in [0,1]
-		real mu2 = 0.0;					///< weight for the quadratic cost on the control in [0,1]
-		real singularControl = -1;		///< singular control value
+		real C = 3.5;
+		real b = 7.0;
+		real KD = 310.0;
+		real kr = 500.0;
+		real u_max = 1.0;
+		real mu1 = 1.0;
+		real mu2 = 0.0;
+		real singularControl = -1;
 	};
 
 	goddard(std::string the_fileTrace = std::string(""), int stepNbr = 10);

@@ -15,23 +15,23 @@ class interceptor:public model
 {
 public:
 	struct parameters_struct{
-		real c0;				///< max curvature at ground level (1/m)
-		real hr;				///< reference altitude (m)
-		real d0;				///< drag at ground level (1/m)
-		real eta;				///< coeff of efficiency
-		real propellant_mass;	///< propellant mass (kg)
-		real empty_mass; 		///< empty mass (kg)
-		real q; 				///< mass flow rate (kg/s)
-		real ve; 				///< gas speed (m/s)
-		real alpha_max; 		///< max angle of attack (rd)
-		real u_max;				///< max of the normalized control (for saturation)
-		real a_max;				///< max acceleration allowed (for saturation)
-		real r_2p;				///< ratio of used gas for the second propulsion phase
-		real t_2p;				///< start time for the second propulsion phase
-		real mu_gft;			///< parameter for considering gravity and propulsion
-		real muT;				///< weight for time cost
-		real muV;				///< weight for velocity cost
-		real muC;				///< weight for quadratic control cost
+		real c0;
+		real hr;
+		real d0;
+		real eta;
+		real propellant_mass;
+		real empty_mass;
+		real q;
+		real ve;
+		real alpha_max;
+		real u_max;
+		real a_max;
+		real r_2p;
+		real t_2p;
+		real mu_gft;
+		real muT;
+		real muV;
+		real muC;
 	};
 
 	interceptor(std::string the_fileTrace = std::string(""));

@@ -12,15 +12,15 @@ class vtolUAV:public model
 {
 public:
 	struct parameters_struct{
-		real u_max;				///< max normalized control
-		real a_max;				///< max acceleration
-		real alphaT;			///< weight for time cost
-		real alphaV;			///< weight for Vd
-		real invSigmaXwp;		///< weight for cost at intermediate points
-		real Vd;				///< desired velocity
-		real ca;				///< drag coefficient
-		int nWP_tot;			///< total number of WP
-		int nWP;				///< current number of WP
+		real u_max;
+		real a_max;
+		real alphaT;
+		real alphaV;
+		real invSigmaXwp;
+		real Vd;
+		real ca;
+		int nWP_tot;
+		int nWP;
 	};
 
 	vtolUAV(map & the_map, std::string the_fileTrace = std::string(""));

@@ -74,6 +74,9 @@ typedef struct {
     double integrate_ms, integrate_launches;   /* integrate_worklist */
     double advance_ms, advance_launches;       /* hybrd_res_kernel + hybrd_jac_kernel (Powell-hybrid step) */
     double assemble_ms;                        /* assemble_kernel (residual / FD Jacobian assembly) */
+    double jac_ms;                             /* hybrd_jac_kernel alone (included in advance_ms) */
+    double iterations;                         /* problem-iterations of hybrd_res_kernel (Broyden steps), device counter */
+    double jac_evals;                          /* Jacobian factorisations of hybrd_jac_kernel, device counter */
 } socp_stats;
 
 /* ---- context ------------------------------------------------------------------------------ */
@@ -109,6 +112,18 @@ int socp_set_obstacles(socp_ctx *ctx, int n, const double *type, const double *p
 int socp_traj_batch(socp_ctx *ctx, int model_id, int step_nbr, long B, const double *mparams,
                     const double *sw, const double *t0, const double *tf, const double *X0,
                     double *Xf, int mem);
+
+/* The observer form of the same integration (odeTools.cpp:103-123 with model::Trace,
+ * model.hpp:446-462; shooting::Trace re-integrates every segment this way, shooting.cpp:496-544):
+ * one row at t0 and one after every RK4 step.  rows is [B][R][W], W = socp_trace_width(model) =
+ * 1 + 2dim + ncontrol + 1 + 1 columns {t, X, control, H, extra}, extra = goddard's switching function
+ * (goddard.cpp:337) / interceptor's chart id (interceptor.cpp:151) / 0; R = socp_trace_max_rows.
+ * nrows[B] receives the rows written per trajectory.  Xf (end points) may be NULL. */
+int socp_trace_width(int model_id);
+int socp_trace_max_rows(int model_id, int step_nbr);
+int socp_trace_batch(socp_ctx *ctx, int model_id, int step_nbr, long B, const double *mparams,
+                     const double *sw, const double *t0, const double *tf, const double *X0,
+                     double *rows, int *nrows, double *Xf, int mem);
 
 /* odeTools::Model / model::Control / model::Hamiltonian at B points (rhs [B][2dim], control
  * [B][4], H [B]); any output may be NULL.  chart_stage: optional [B][2] ints (interceptor). */

@@ -767,10 +767,19 @@ static void so_rhs_exact(so_problem *p, double t, const double *X, double *dX);
 
 void so_rhs(so_problem *p, double t, const double *X, double *dX)
 {
-    so_rhs_exact(p, t, X, dX);
-    if (p->noise_ulps > 0)
+    if (p->noise_ulps > 0) {
+        /* backward-error model of a different libm / FMA contraction: the formulas are evaluated at
+         * inputs moved by a few ulp (this is what carries rounding through cancellations such as
+         * the singular control, goddard.cpp:188-253) and every output is moved by a few ulp */
+        double Y[2 * SO_MAX_DIM];
+        for (int i = 0; i < 2 * p->dim; ++i)
+            Y[i] = X[i] * (1.0 + p->noise_ulps * 1.1102230246251565e-16 * noise_u(p));
+        so_rhs_exact(p, t, Y, dX);
         for (int i = 0; i < 2 * p->dim; ++i)
             dX[i] *= 1.0 + p->noise_ulps * 1.1102230246251565e-16 * noise_u(p);
+        return;
+    }
+    so_rhs_exact(p, t, X, dX);
 }
 
 static void so_rhs_exact(so_problem *p, double t, const double *X, double *dX)
@@ -800,7 +809,20 @@ int so_control(so_problem *p, double t, const double *X, double *u)
     return 0;
 }
 
+static double so_hamiltonian_exact(so_problem *p, double t, const double *X);
+
 double so_hamiltonian(so_problem *p, double t, const double *X)
+{
+    if (p->noise_ulps > 0) {           /* conditioning probe, same model as so_rhs */
+        double Y[2 * SO_MAX_DIM];
+        for (int i = 0; i < 2 * p->dim; ++i)
+            Y[i] = X[i] * (1.0 + p->noise_ulps * 1.1102230246251565e-16 * noise_u(p));
+        return so_hamiltonian_exact(p, t, Y) * (1.0 + p->noise_ulps * 1.1102230246251565e-16 * noise_u(p));
+    }
+    return so_hamiltonian_exact(p, t, X);
+}
+
+static double so_hamiltonian_exact(so_problem *p, double t, const double *X)
 {
     switch (p->model_id) {
     case SO_GODDARD: return goddard_H(p, t, X);

@@ -49,9 +49,10 @@ typedef struct {
     int chart, stage;                       /* interceptor.cpp:27-29 */
     /* statistics */
     long rk4_steps;
-    /* conditioning probe (tests only): when noise_ulps > 0 every RHS component is multiplied by
-     * (1 + noise_ulps * 2^-53 * u), u uniform in [-1,1] -- a stochastic-arithmetic estimate of how
-     * far a libm / FMA difference of that many ulps can move a trajectory */
+    /* conditioning probe (tests only): when noise_ulps > 0 every RHS / Hamiltonian evaluation
+     * happens at inputs multiplied component-wise by (1 + noise_ulps * 2^-53 * u), u uniform in
+     * [-1,1], and every output is multiplied likewise -- a stochastic-arithmetic (backward error)
+     * estimate of how far a libm / FMA difference of that many ulps can move a result */
     double noise_ulps;
     unsigned long long noise_state;
 } so_problem;

@@ -24,7 +24,8 @@ class Stats(ctypes.Structure):
                 ("solver_rounds", ctypes.c_double), ("device_bytes", ctypes.c_double),
                 ("integrate_ms", ctypes.c_double), ("integrate_launches", ctypes.c_double),
                 ("advance_ms", ctypes.c_double), ("advance_launches", ctypes.c_double),
-                ("assemble_ms", ctypes.c_double)]
+                ("assemble_ms", ctypes.c_double), ("jac_ms", ctypes.c_double),
+                ("iterations", ctypes.c_double), ("jac_evals", ctypes.c_double)]
 
 
 _LIB = None

@@ -52,7 +52,7 @@ struct socp_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int sm_count = 0;
     int profile = 0;
-    double integrate_ms = 0, integrate_launches = 0, advance_ms = 0, advance_launches = 0, assemble_ms = 0;
+    double integrate_ms = 0, integrate_launches = 0, advance_ms = 0, advance_launches = 0, assemble_ms = 0, jac_ms = 0;
     std::vector<cudaEvent_t> prof_events;
     SolverWorkspace solver;              // persistent state of the batched solver (solver.cuh)
 };
@@ -126,6 +126,13 @@ static void launch_traj(socp_ctx *ctx, long B, int S, const double *mp, const do
     const int threads = 128;
     long blocks = (B + threads - 1) / threads;
     traj_kernel<MODEL><<<(unsigned)blocks, threads, 0, ctx->stream>>>(B, S, mp, sw, t0, tf, X0, Xf, ctx->d_counters);
+    ctx->launches += 1;
+}
+
+template <int MODEL>
+static void launch_trace(socp_ctx *ctx, long B, int S, int max_rows, const double *mp, const double *sw, const double *t0,
+                         const double *tf, const double *X0, double *rows, int *nrows, double *Xf) {
+    trace_kernel<MODEL><<<(unsigned)((B + 63) / 64), 64, 0, ctx->stream>>>(B, S, max_rows, mp, sw, t0, tf, X0, rows, nrows, Xf);
     ctx->launches += 1;
 }
 
@@ -238,6 +245,9 @@ int socp_get_stats(socp_ctx *ctx, socp_stats *out) {
     out->integrate_ms = ctx->integrate_ms; out->integrate_launches = ctx->integrate_launches;
     out->advance_ms = ctx->advance_ms; out->advance_launches = ctx->advance_launches;
     out->assemble_ms = ctx->assemble_ms;
+    out->jac_ms = ctx->jac_ms;
+    out->iterations = (double)c[1];
+    out->jac_evals = (double)c[2];
     return SOCP_OK;
 }
 
@@ -246,7 +256,7 @@ int socp_reset_stats(socp_ctx *ctx) {
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
     ctx->launches = 0;
     ctx->rounds = 0;
-    ctx->integrate_ms = ctx->integrate_launches = ctx->advance_ms = ctx->advance_launches = ctx->assemble_ms = 0;
+    ctx->integrate_ms = ctx->integrate_launches = ctx->advance_ms = ctx->advance_launches = ctx->assemble_ms = ctx->jac_ms = 0;
     return SOCP_OK;
 }
 
@@ -310,6 +320,52 @@ int socp_traj_batch(socp_ctx *ctx, int model_id, int step_nbr, long B, const dou
     case SOCP_INTERCEPTOR: launch_traj<INTERCEPTOR>(ctx, B, S, d_mp, d_sw, d_t0, d_tf, d_X0, d_Xf); break;
     }
     CUDA_TRY(ctx, cudaGetLastError());
+    if ((rc = fetch_out(ctx, Xf, d_Xf, (size_t)B * N, mem)) != SOCP_OK) return rc;
+    if (mem == SOCP_HOST) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return SOCP_OK;
+}
+
+int socp_trace_width(int id) {
+    static const int nctrl[SOCP_NUM_MODELS] = {3, 3, 1, 3, 2};
+    return (id >= 0 && id < SOCP_NUM_MODELS) ? 2 * kDim[id] + nctrl[id] + 3 : SOCP_ERR_ARG;
+}
+int socp_trace_max_rows(int id, int step_nbr) {
+    if (id < 0 || id >= SOCP_NUM_MODELS) return SOCP_ERR_ARG;
+    const int S = step_nbr > 0 ? step_nbr : kSteps[id];
+    return (S + 1) * (id == SOCP_INTERCEPTOR ? 2 : 1);
+}
+
+int socp_trace_batch(socp_ctx *ctx, int model_id, int step_nbr, long B, const double *mparams,
+                     const double *sw, const double *t0, const double *tf, const double *X0,
+                     double *rows, int *nrows, double *Xf, int mem) {
+    if (!ctx) return SOCP_ERR_ARG;
+    if (model_id < 0 || model_id >= SOCP_NUM_MODELS || B < 0 || !mparams || !t0 || !tf || !X0 || !rows || !nrows)
+        return fail(ctx, SOCP_ERR_ARG, "socp_trace_batch: bad arguments");
+    if (B == 0) return SOCP_OK;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const int N = 2 * kDim[model_id], np = kNP[model_id];
+    const int S = step_nbr > 0 ? step_nbr : kSteps[model_id];
+    const int W = socp_trace_width(model_id), R = socp_trace_max_rows(model_id, S);
+    int rc = SOCP_OK;
+    const double *d_mp = stage_in(ctx, SLOT_MPARAMS, mparams, (size_t)B * np, mem, &rc);
+    const double *d_sw = stage_in(ctx, SLOT_SW, sw, (size_t)B * 2, mem, &rc);
+    const double *d_t0 = stage_in(ctx, SLOT_T0, t0, (size_t)B, mem, &rc);
+    const double *d_tf = stage_in(ctx, SLOT_TF, tf, (size_t)B, mem, &rc);
+    const double *d_X0 = stage_in(ctx, SLOT_X0, X0, (size_t)B * N, mem, &rc);
+    double *d_rows = stage_out(ctx, SLOT_AUX0, rows, (size_t)B * R * W, mem, &rc);
+    int *d_nr = stage_out(ctx, SLOT_INFO, nrows, (size_t)B, mem, &rc);
+    double *d_Xf = stage_out(ctx, SLOT_XF, Xf, (size_t)B * N, mem, &rc);
+    if (rc != SOCP_OK) return rc;
+    switch (model_id) {
+    case SOCP_GODDARD: launch_trace<GODDARD>(ctx, B, S, R, d_mp, d_sw, d_t0, d_tf, d_X0, d_rows, d_nr, d_Xf); break;
+    case SOCP_DOUBLE_INTEGRATOR: launch_trace<DOUBLE_INTEGRATOR>(ctx, B, S, R, d_mp, d_sw, d_t0, d_tf, d_X0, d_rows, d_nr, d_Xf); break;
+    case SOCP_COVID19: launch_trace<COVID19>(ctx, B, S, R, d_mp, d_sw, d_t0, d_tf, d_X0, d_rows, d_nr, d_Xf); break;
+    case SOCP_VTOL_UAV: launch_trace<VTOL_UAV>(ctx, B, S, R, d_mp, d_sw, d_t0, d_tf, d_X0, d_rows, d_nr, d_Xf); break;
+    case SOCP_INTERCEPTOR: launch_trace<INTERCEPTOR>(ctx, B, S, R, d_mp, d_sw, d_t0, d_tf, d_X0, d_rows, d_nr, d_Xf); break;
+    }
+    CUDA_TRY(ctx, cudaGetLastError());
+    if ((rc = fetch_out(ctx, rows, d_rows, (size_t)B * R * W, mem)) != SOCP_OK) return rc;
+    if ((rc = fetch_out(ctx, nrows, d_nr, (size_t)B, mem)) != SOCP_OK) return rc;
     if ((rc = fetch_out(ctx, Xf, d_Xf, (size_t)B * N, mem)) != SOCP_OK) return rc;
     if (mem == SOCP_HOST) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return SOCP_OK;

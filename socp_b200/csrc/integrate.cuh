@@ -130,6 +130,101 @@ traj_kernel(long B, int S, const double *__restrict__ mparams, const double *__r
     count_steps(counter, steps);
 }
 
+// ---- kernel: trajectories with the observer (model::Trace rows) ----------------------------------
+// Restates the observer form of odeTools::integrate (odeTools.cpp:103-123): one row at t0 and one
+// after every RK4 step.  Row layout = model::Trace (model.hpp:446-462): t, X[0..N), control[0..NCTRL),
+// H, extra -- extra is the switching function of goddard::Trace (goddard.cpp:337-339), the chart id
+// of interceptor::Trace (interceptor.cpp:151), 0 otherwise.
+template <int MODEL> SOCP_DEV double trace_extra(const typename Model<MODEL>::Ctx &, const double *) { return 0.0; }
+template <> SOCP_DEV double trace_extra<GODDARD>(const Model<GODDARD>::Ctx &c, const double *X) {
+    return c.mu1 - c.b * X[13] - c.C / X[6] * sqrt(X[10] * X[10] + X[11] * X[11] + X[12] * X[12]);
+}
+template <> SOCP_DEV double trace_extra<INTERCEPTOR>(const Model<INTERCEPTOR>::Ctx &c, const double *) { return (double)c.chart; }
+
+template <int MODEL>
+__device__ __noinline__ void trace_row(const typename Model<MODEL>::Ctx &c, double t, const double *X, double *row) {
+    typedef Model<MODEL> M;
+    constexpr int N = M::N;
+    row[0] = t;
+    for (int i = 0; i < N; ++i) row[1 + i] = X[i];
+    double u[4] = {0, 0, 0, 0};
+    M::control(c, t, X, u);
+    for (int k = 0; k < M::NCTRL; ++k) row[1 + N + k] = u[k];
+    row[1 + N + M::NCTRL] = M::hamiltonian(c, t, X);
+    row[2 + N + M::NCTRL] = trace_extra<MODEL>(c, X);
+}
+
+template <int MODEL>
+SOCP_DEV int trace_traj(typename Model<MODEL>::Ctx &c, double *X, double t0, double tf, int S, double *rows, int W) {
+    const double dt = (tf - t0) / S;
+    double t = t0;
+    int nr = 0;
+    trace_row<MODEL>(c, t, X, rows + (size_t)(nr++) * W);
+    while (t < (tf - dt / 2)) {
+        if (t + dt > tf) rk4_step<MODEL>(c, t, X, tf - t);
+        else rk4_step<MODEL>(c, t, X, dt);
+        t += dt;
+        trace_row<MODEL>(c, t, X, rows + (size_t)(nr++) * W);
+    }
+    return nr;
+}
+
+SOCP_DEV int interceptor_trace_int(Model<INTERCEPTOR>::Ctx &c, double *X, double t0, double tf, int S, double *rows, int W) {
+    double t = t0;
+    const double dt = (tf - t0) / S;
+    int nr = 0;
+    trace_row<INTERCEPTOR>(c, t, X, rows + (size_t)(nr++) * W);
+    for (int i = 0; i < S; ++i) {
+        Model<INTERCEPTOR>::set_chart(c, X);
+        rk4_step<INTERCEPTOR>(c, t, X, dt);
+        t += dt;
+        trace_row<INTERCEPTOR>(c, t, X, rows + (size_t)(nr++) * W);
+    }
+    return nr;
+}
+
+template <>
+SOCP_DEV int trace_traj<INTERCEPTOR>(Model<INTERCEPTOR>::Ctx &c, double *X, double t0, double tf, int S, double *rows, int W) {
+    int nr = 0;
+    c.chart = 1;
+    const double t1 = c.mprop / c.q;
+    if (t0 < t1) {
+        c.stage = 1;
+        if (tf > t1) {
+            nr += interceptor_trace_int(c, X, t0, t1, S, rows, W);
+            c.stage = 0;
+            nr += interceptor_trace_int(c, X, t1, tf, S, rows + (size_t)nr * W, W);
+        } else {
+            nr += interceptor_trace_int(c, X, t0, tf, S, rows, W);
+        }
+    } else {
+        c.stage = 0;
+        nr += interceptor_trace_int(c, X, t0, tf, S, rows, W);
+    }
+    if (c.chart == 2) Model<INTERCEPTOR>::convert(2, X);
+    return nr;
+}
+
+// rows: [B][max_rows][W]; nrows[b] = rows written (S+1 per integration, two integrations for a
+// two-stage interceptor flight); Xf as traj_kernel.
+template <int MODEL>
+__global__ void __launch_bounds__(64)
+trace_kernel(long B, int S, int max_rows, const double *__restrict__ mparams, const double *__restrict__ sw,
+             const double *__restrict__ t0, const double *__restrict__ tf, const double *__restrict__ X0,
+             double *__restrict__ rows, int *__restrict__ nrows, double *__restrict__ Xf) {
+    typedef Model<MODEL> M;
+    constexpr int N = M::N, W = N + M::NCTRL + 3;
+    long b = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    typename M::Ctx c;
+    M::load(c, mparams + b * M::NP, sw ? sw + 2 * b : nullptr);
+    double X[N];
+    for (int i = 0; i < N; ++i) X[i] = X0[b * N + i];
+    const int nr = trace_traj<MODEL>(c, X, t0[b], tf[b], S, rows + (size_t)b * max_rows * W, W);
+    nrows[b] = nr;
+    if (Xf) for (int i = 0; i < N; ++i) Xf[b * N + i] = X[i];
+}
+
 // ---- kernel: RHS / control / Hamiltonian at B points -----------------------------------------
 template <int MODEL>
 __global__ void point_kernel(long B, const double *__restrict__ mparams, const double *__restrict__ sw,

@@ -501,22 +501,33 @@ __device__ void dogleg_g(int n, const double *r, const double *diag, const doubl
     const int tid = threadIdx.x % G;
     const int lane = threadIdx.x & 31;
     gsync<G>();
-    // Gauss-Newton direction: back substitution row by row from the bottom, on one warp
+    // Gauss-Newton direction R x = qtb by back substitution, column-oriented so that the only value
+    // on the sequential chain is x[j] itself: each lane of warp 0 owns the rows i = lane (mod 32) and
+    // keeps their running right-hand sides in x[i]; x[j] travels by one shuffle per step and the
+    // right-hand side of the next pivot row is carried in a register.  The effective diagonal
+    // (MINPACK replaces a zero pivot by epsmch * max|column|) is prepared in wa2 by all threads.
+    for (int j = tid; j < n; j += G) {
+        double temp = r[rowstart(n, j)];
+        if (temp == 0.) {
+            int l = j;
+            for (int i = 0; i <= j; ++i) { temp = fmax(temp, fabs(r[l])); l += n - 1 - i; }
+            temp = EPSMCH * temp;
+            if (temp == 0.) temp = EPSMCH;
+        }
+        wa2[j] = temp;
+        x[j] = qtb[j];
+    }
+    gsync<G>();
     if (tid < 32) {
+        double bj = x[n - 1];                                  // rhs of the pivot row (owner lane)
         for (int j = n - 1; j >= 0; --j) {
-            const int jj = rowstart(n, j);
-            double part = 0.;
-            for (int i = j + 1 + lane; i < n; i += 32) part += r[jj + (i - j)] * x[i];
-            const double sum = warp_sum(part);
-            double temp = r[jj];
-            if (temp == 0.) {
-                int l = j;
-                for (int i = 0; i <= j; ++i) { temp = fmax(temp, fabs(r[l])); l += n - 1 - i; }
-                temp = EPSMCH * temp;
-                if (temp == 0.) temp = EPSMCH;
-            }
-            if (lane == 0) x[j] = (qtb[j] - sum) / temp;
-            __syncwarp();
+            const int owner = j & 31, next_owner = (j - 1) & 31;
+            double cr = 0., cx = 0.;                           // next pivot row: fetched before x[j] is known
+            if (j > 0 && lane == next_owner) { cr = r[rowstart(n, j - 1) + 1]; cx = x[j - 1]; }
+            const double xj = __shfl_sync(0xffffffffu, bj / wa2[j], owner);
+            if (lane == owner) x[j] = xj;
+            if (j > 0 && lane == next_owner) { bj = cx - cr * xj; x[j - 1] = bj; }
+            for (int i = lane; i < j - 1; i += 32) x[i] -= r[rowstart(n, i) + (j - i)] * xj;
         }
     }
     gsync<G>();
@@ -554,40 +565,107 @@ __device__ void dogleg_g(int n, const double *r, const double *diag, const doubl
     gsync<G>();
 }
 
+// Givens rotation that maps (a, b) to (rho, 0) with MINPACK's conventions (r1updt): the coefficient
+// of the larger operand is positive.  One rsqrt instead of MINPACK's divide / sqrt / divide keeps
+// the sequential chains short; when a square could leave the double range the ratio form is used.
+SOCP_DEV void givens(double a, double b, double &c, double &sgl) {
+    const double mx = fmax(fabs(a), fabs(b));
+    if (mx < 1e140 && mx > 1e-140) {
+        const double rinv = rsqrt(a * a + b * b);
+        if (fabs(a) < fabs(b)) { sgl = fabs(b) * rinv; c = copysign(a * rinv, a) * copysign(1., b); }
+        else { c = fabs(a) * rinv; sgl = copysign(b * rinv, b) * copysign(1., a); }
+    } else if (fabs(a) < fabs(b)) {
+        const double cotan = a / b;
+        sgl = .5 / sqrt(.25 + .25 * (cotan * cotan));
+        c = sgl * cotan;
+    } else {
+        const double tn = b / a;
+        c = .5 / sqrt(.25 + .25 * (tn * tn));
+        sgl = c * tn;
+    }
+}
+// what r1mpyq needs to rebuild the rotation (MINPACK's tau)
+SOCP_DEV double givens_tau(double a, double b, double c, double sgl) {
+    if (fabs(a) < fabs(b)) return (fabs(c) * DBL_MAX > 1.) ? 1. / c : 1.;
+    return sgl;
+}
+
 // r1updt on the packed upper-triangular factor (m == n): (R + u v^T) -> R' with the 2(n-1) Givens
-// rotations recorded in v and w for r1mpyq.  cs/sn are scratch [n] each.
+// rotations recorded in v and w for r1mpyq.  cs/sn are scratch [n] each, tmp is scratch [2n].
 template <int G>
-__device__ void r1updt_g(int n, double *s, const double *u, double *v, double *w, double *cs, double *sn) {
+__device__ void r1updt_g(int n, double *s, const double *u, double *v, double *w, double *cs, double *sn, double *tmp) {
     const int tid = threadIdx.x % G;
     const int lane = threadIdx.x & 31;
-    const double giant = DBL_MAX;
+    const unsigned FULL = 0xffffffffu;
     gsync<G>();
-    // first sweep: the rotation coefficients depend on v only (scalar recurrence on v[n-1])
-    if (tid == 0) {
-        double vn = v[n - 1];
-        for (int j = n - 2; j >= 0; --j) {
-            const double vj = v[j];
-            double c = 2., sgl = 0.;               // c == 2 marks "no rotation"
-            if (vj != 0.) {
-                double tau;
-                if (fabs(vn) < fabs(vj)) {
-                    const double cotan = vn / vj;
-                    sgl = .5 / sqrt(.25 + .25 * (cotan * cotan));
-                    c = sgl * cotan;
-                    tau = 1.;
-                    if (fabs(c) * giant > 1.) tau = 1. / c;
-                } else {
-                    const double tn = vj / vn;
-                    c = .5 / sqrt(.25 + .25 * (tn * tn));
-                    sgl = c * tn;
-                    tau = sgl;
-                }
-                vn = sgl * vj + c * vn;
-                v[j] = tau;
+    // First sweep (j = n-2 .. 0).  Rotation j is built from v[j] and the running value vn, which
+    // before step j is +-sqrt(sum_{k > j} v[k]^2) carrying the sign of the entry that last dominated
+    // (|vn| < |v[k]|), or of v[n-1].  Both are suffix scans, so warp 0 forms all rotations at once
+    // instead of walking the scalar recurrence.
+    if (tid < 32) {
+        double *SS = tmp;                              // SS[k] = sum_{q >= k} v[q]^2
+        int *IDX = (int *)(tmp + n);                   // smallest dominating index above k within the lane's chunk
+        double *TAU = w;                               // w is written only after this phase
+        const int per = (n + 31) >> 5;                 // contiguous chunk of indices per lane
+        const int lo = min(lane * per, n), hi = min(lo + per, n);
+        double vmax = 0.;
+        for (int k = lo; k < hi; ++k) vmax = fmax(vmax, fabs(v[k]));
+        for (int off = 16; off > 0; off >>= 1) vmax = fmax(vmax, __shfl_xor_sync(FULL, vmax, off));
+        if (vmax < 1e140 && (vmax > 1e-140 || vmax == 0.)) {
+            double acc = 0.;
+            for (int k = hi - 1; k >= lo; --k) { acc += v[k] * v[k]; SS[k] = acc; }
+            double run = acc;                          // inclusive suffix scan over the lanes
+            for (int off = 1; off < 32; off <<= 1) {
+                const double t = __shfl_down_sync(FULL, run, off);
+                if (lane + off < 32) run += t;
             }
-            cs[j] = c; sn[j] = sgl;
+            double above = __shfl_down_sync(FULL, run, 1);
+            if (lane == 31) above = 0.;
+            for (int k = lo; k < hi; ++k) SS[k] += above;
+            __syncwarp();
+            int best = n - 1;                          // smallest dominating index in this chunk so far
+            for (int k = min(hi - 1, n - 2); k >= lo; --k) {
+                IDX[k] = best;
+                if (v[k] != 0. && sqrt(SS[k + 1]) < fabs(v[k])) best = k;
+            }
+            int runm = best;
+            for (int off = 1; off < 32; off <<= 1) {
+                const int t = __shfl_down_sync(FULL, runm, off);
+                if (lane + off < 32) runm = min(runm, t);
+            }
+            int upm = __shfl_down_sync(FULL, runm, 1); // smallest dominating index above this chunk
+            if (lane == 31) upm = n - 1;
+            for (int k = min(hi - 1, n - 2); k >= lo; --k) {
+                const double vj = v[k];
+                double c = 2., sgl = 0., tau = 0.;     // c == 2 marks "no rotation"
+                if (vj != 0.) {
+                    const int src = (IDX[k] != n - 1) ? IDX[k] : upm;
+                    const double m = copysign(sqrt(SS[k + 1]), v[src]);
+                    givens(m, vj, c, sgl);
+                    tau = givens_tau(m, vj, c, sgl);
+                }
+                cs[k] = c; sn[k] = sgl; TAU[k] = tau;
+            }
+            double vn_final = 0.;
+            if (lane == 0) vn_final = copysign(sqrt(SS[0]), v[runm]);
+            __syncwarp();                              // every read of v is done
+            for (int k = min(hi - 1, n - 2); k >= lo; --k) if (cs[k] < 1.5) v[k] = TAU[k];
+            if (lane == 0) v[n - 1] = vn_final;
+        } else if (lane == 0) {
+            // badly scaled vector: MINPACK's scalar recurrence
+            double vn = v[n - 1];
+            for (int j = n - 2; j >= 0; --j) {
+                const double vj = v[j];
+                double c = 2., sgl = 0.;
+                if (vj != 0.) {
+                    givens(vn, vj, c, sgl);
+                    v[j] = givens_tau(vn, vj, c, sgl);
+                    vn = sgl * vj + c * vn;
+                }
+                cs[j] = c; sn[j] = sgl;
+            }
+            v[n - 1] = vn;
         }
-        v[n - 1] = vn;
     }
     gsync<G>();
     // apply to the columns: column i is touched by rotations j = min(i, n-2) .. 0
@@ -604,37 +682,35 @@ __device__ void r1updt_g(int n, double *s, const double *u, double *v, double *w
         w[i] = wi + v[n - 1] * u[i];                 // add the spike from the rank-1 update
     }
     gsync<G>();
-    // second sweep: eliminate the spike; rotation j depends on w[j] after rotations 0..j-1.
-    // Strictly sequential in j: run it on one warp (warp barriers only).
+    // Second sweep: eliminate the spike; rotation j depends on w[j] after rotations 0..j-1, strictly
+    // sequential in j.  Warp 0: each lane owns the columns i = lane (mod 32) for the whole sweep (no
+    // barrier inside the loop); the pivot w[j+1] is carried in a register and broadcast by one shuffle.
     if (tid < 32) {
+        double wj = w[0];
+        double sjj = s[0];
         for (int j = 0; j < n - 1; ++j) {
             const int jj = rowstart(n, j);
-            const double wj = w[j], sjj = s[jj];
-            __syncwarp();
-            if (wj != 0.) {
-                double c, sgl, tau;
-                if (fabs(sjj) < fabs(wj)) {
-                    const double cotan = sjj / wj;
-                    sgl = .5 / sqrt(.25 + .25 * (cotan * cotan));
-                    c = sgl * cotan;
-                    tau = 1.;
-                    if (fabs(c) * giant > 1.) tau = 1. / c;
-                } else {
-                    const double tn = wj / sjj;
-                    c = .5 / sqrt(.25 + .25 * (tn * tn));
-                    sgl = c * tn;
-                    tau = sgl;
-                }
-                for (int i = j + lane; i < n; i += 32) {
+            const int nown = (j + 1) & 31;                         // owner of the next pivot
+            double c1 = 0., c2 = 0.;
+            if (lane == nown) { c1 = s[jj + 1]; c2 = w[j + 1]; }   // fetched before the rotation is known
+            const double sjj_next = s[rowstart(n, j + 1)];         // row j+1 is untouched until step j+1
+            double carry = c2;
+            if (wj != 0.) {                                        // uniform: wj is the same in every lane
+                double c, sgl;
+                givens(sjj, wj, c, sgl);
+                if (lane == (j & 31)) { s[jj] = c * sjj + sgl * wj; w[j] = givens_tau(sjj, wj, c, sgl); }
+                if (lane == nown) { s[jj + 1] = c * c1 + sgl * c2; carry = -sgl * c1 + c * c2; w[j + 1] = carry; }
+                for (int i = j + 2 + ((lane - j - 2) & 31); i < n; i += 32) {
                     const int l = jj + (i - j);
                     const double sl = s[l], wi = w[i];
                     s[l] = c * sl + sgl * wi;
-                    w[i] = (i == j) ? tau : (-sgl * sl + c * wi);
+                    w[i] = -sgl * sl + c * wi;
                 }
             }
-            __syncwarp();
+            wj = __shfl_sync(FULL, carry, nown);
+            sjj = sjj_next;
         }
-        if (lane == 0) s[rowstart(n, n - 1)] = w[n - 1];
+        if (lane == ((n - 1) & 31)) s[rowstart(n, n - 1)] = w[n - 1];
     }
     gsync<G>();
 }
@@ -886,7 +962,8 @@ hybrd_res_kernel(SolverDev D, int cur, int per_group_doubles) {
                     }
                 }
             }
-            r1updt_g<G>(n, W.r, W.wa1, W.wa2, W.wa3, W.scr, W.scr + n);
+            if (tid == 0) atomicAdd(D.counters + 1, 1ULL);
+            r1updt_g<G>(n, W.r, W.wa1, W.wa2, W.wa3, W.scr, W.scr + n, W.scr + 2 * n);
             r1coef_g<G>(n, W.wa2, W.wa3, W.scr);
             r1mpyq_g<G>(n, n, W.q, W.ldq, W.scr);
             r1mpyq_g<G>(1, n, W.qtf, 1, W.scr);
@@ -941,7 +1018,7 @@ hybrd_jac_kernel(SolverDev D, int cur, int per_group_doubles) {
         if (STAGE_Q)
             for (int e = tid; e < n * n; e += G) W.q[(e % n) + (size_t)(e / n) * ldq_s] = gq[e];
         gsync<G>();
-        if (tid == 0) { is[I_NFEV] += n; is[I_JEVAL] = 1; }
+        if (tid == 0) { is[I_NFEV] += n; is[I_JEVAL] = 1; atomicAdd(D.counters + 2, 1ULL); }
         for (int i = tid; i < n; i += G) W.qtf[i] = W.fvec[i];
         // wa1 = rdiag, wa2 = acnorm
         qrfac_g<G>(n, W.q, W.ldq, W.wa1, W.wa2, W.qtf, red);

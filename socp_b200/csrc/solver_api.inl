@@ -95,7 +95,7 @@ size_t carve(HostPlan &pl, void *blob, long Bw) {
 }
 
 const int kProfSlots = 16;      // rounds between two harvests of the profiling events
-const int kProfEv = 4;          // events per profiled round
+const int kProfEv = 5;          // events per profiled round
 
 cudaEvent_t prof_event(socp_ctx *ctx, int idx) {
     while ((int)ctx->prof_events.size() <= idx) {
@@ -109,13 +109,15 @@ cudaEvent_t prof_event(socp_ctx *ctx, int idx) {
 // accumulate the per-kernel times of the last `n` profiled rounds (events must have completed)
 void prof_harvest(socp_ctx *ctx, int n) {
     for (int k = 0; k < n; ++k) {
-        float a = 0, b = 0, c = 0;
+        float a = 0, b = 0, c = 0, d = 0;
         cudaEventElapsedTime(&a, ctx->prof_events[kProfEv * k], ctx->prof_events[kProfEv * k + 1]);
         cudaEventElapsedTime(&b, ctx->prof_events[kProfEv * k + 1], ctx->prof_events[kProfEv * k + 2]);
         cudaEventElapsedTime(&c, ctx->prof_events[kProfEv * k + 2], ctx->prof_events[kProfEv * k + 3]);
         ctx->integrate_ms += a; ctx->integrate_launches += 1;
         ctx->assemble_ms += b;
-        ctx->advance_ms += c; ctx->advance_launches += 2;
+        cudaEventElapsedTime(&d, ctx->prof_events[kProfEv * k + 3], ctx->prof_events[kProfEv * k + 4]);
+        ctx->advance_ms += c + d; ctx->advance_launches += 2;
+        ctx->jac_ms += d;
     }
 }
 
@@ -164,19 +166,21 @@ void launch_smem(K kernel, int grid, int threads, size_t smem, cudaStream_t st, 
     kernel<<<grid, threads, smem, st>>>(D, cur, doubles);
 }
 
-void launch_hybrd(socp_ctx *ctx, const SolverDev &D, int cur, int grid) {
+void launch_hybrd(socp_ctx *ctx, const SolverDev &D, int cur, int grid, int prof_slot) {
     const SmemPlan sp = smem_plan(D);
     const int thr = (sp.G == 32) ? 32 * sp.groups : 128;
     const int g = (sp.G == 32) ? grid * (4 / sp.groups) : grid;
     if (sp.G == 32) {
         if (sp.stage_r) launch_smem(hybrd_res_kernel<32, true>, g, thr, sp.bytes_res, ctx->stream, D, cur, sp.doubles_res);
         else launch_smem(hybrd_res_kernel<32, false>, g, thr, sp.bytes_res, ctx->stream, D, cur, sp.doubles_res);
+        if (prof_slot >= 0) cudaEventRecord(prof_event(ctx, kProfEv * prof_slot + 3), ctx->stream);
         if (sp.stage_q_jac) launch_smem(hybrd_jac_kernel<32, true, true>, g, thr, sp.bytes_jac, ctx->stream, D, cur, sp.doubles_jac);
         else if (sp.stage_r) launch_smem(hybrd_jac_kernel<32, true, false>, g, thr, sp.bytes_jac, ctx->stream, D, cur, sp.doubles_jac);
         else launch_smem(hybrd_jac_kernel<32, false, false>, g, thr, sp.bytes_jac, ctx->stream, D, cur, sp.doubles_jac);
     } else {
         if (sp.stage_r) launch_smem(hybrd_res_kernel<128, true>, g, thr, sp.bytes_res, ctx->stream, D, cur, sp.doubles_res);
         else launch_smem(hybrd_res_kernel<128, false>, g, thr, sp.bytes_res, ctx->stream, D, cur, sp.doubles_res);
+        if (prof_slot >= 0) cudaEventRecord(prof_event(ctx, kProfEv * prof_slot + 3), ctx->stream);
         if (sp.stage_q_jac) launch_smem(hybrd_jac_kernel<128, true, true>, g, thr, sp.bytes_jac, ctx->stream, D, cur, sp.doubles_jac);
         else if (sp.stage_r) launch_smem(hybrd_jac_kernel<128, true, false>, g, thr, sp.bytes_jac, ctx->stream, D, cur, sp.doubles_jac);
         else launch_smem(hybrd_jac_kernel<128, false, false>, g, thr, sp.bytes_jac, ctx->stream, D, cur, sp.doubles_jac);
@@ -190,8 +194,8 @@ void launch_round(socp_ctx *ctx, const SolverDev &D, int cur, int grid_int, int 
     if (prof_slot >= 0) cudaEventRecord(prof_event(ctx, kProfEv * prof_slot + 1), ctx->stream);
     assemble_kernel<MODEL><<<grid_int, 128, 0, ctx->stream>>>(D, cur);
     if (prof_slot >= 0) cudaEventRecord(prof_event(ctx, kProfEv * prof_slot + 2), ctx->stream);
-    launch_hybrd(ctx, D, cur, grid_adv);
-    if (prof_slot >= 0) cudaEventRecord(prof_event(ctx, kProfEv * prof_slot + 3), ctx->stream);
+    launch_hybrd(ctx, D, cur, grid_adv, prof_slot);
+    if (prof_slot >= 0) cudaEventRecord(prof_event(ctx, kProfEv * prof_slot + 4), ctx->stream);
     ctx->launches += 4;
     ctx->rounds += 1;
 }

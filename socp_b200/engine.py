@@ -143,7 +143,7 @@ class Engine:
         return dict(rk4_steps=s.rk4_steps, kernel_launches=s.kernel_launches,
                     solver_rounds=s.solver_rounds, device_bytes=s.device_bytes,
                     integrate_ms=s.integrate_ms, integrate_launches=s.integrate_launches,
-                    advance_ms=s.advance_ms, advance_launches=s.advance_launches, assemble_ms=s.assemble_ms)
+                    advance_ms=s.advance_ms, advance_launches=s.advance_launches, assemble_ms=s.assemble_ms, jac_ms=s.jac_ms, iterations=s.iterations, jac_evals=s.jac_evals)
 
     def set_profiling(self, on=True):
         self._check(self._L.socp_set_profiling(self._h, int(bool(on))))
