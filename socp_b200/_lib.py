@@ -34,7 +34,7 @@ SYMBOLS = ["socp_create", "socp_destroy", "socp_last_error", "socp_set_stream", 
            "socp_get_stats", "socp_reset_stats", "socp_set_profiling", "socp_timer_start", "socp_timer_stop",
            "socp_model_dim", "socp_model_nparams", "socp_model_default_steps",
            "socp_model_default_params", "socp_num_param", "socp_set_obstacles", "socp_traj_batch",
-           "socp_point_batch", "socp_residual_batch", "socp_fdjac_batch", "socp_solve_batch",
+           "socp_trace_width", "socp_trace_max_rows", "socp_trace_batch", "socp_point_batch", "socp_residual_batch", "socp_fdjac_batch", "socp_solve_batch",
            "socp_continuation_param_batch", "socp_continuation_boundary_batch",
            "socp_measure_fp64_peak"]
 
@@ -69,6 +69,9 @@ def lib():
     L.socp_num_param.argtypes = [sp]
     L.socp_set_obstacles.argtypes = [vp, ci, vp, vp, vp]
     L.socp_traj_batch.argtypes = [vp, ci, ci, cl, vp, vp, vp, vp, vp, vp, ci]
+    L.socp_trace_width.argtypes = [ci]
+    L.socp_trace_max_rows.argtypes = [ci, ci]
+    L.socp_trace_batch.argtypes = [vp, ci, ci, cl, vp, vp, vp, vp, vp, vp, vp, vp, ci]
     L.socp_point_batch.argtypes = [vp, ci, cl, vp, vp, vp, vp, vp, vp, vp, vp, ci]
     L.socp_residual_batch.argtypes = [vp, sp, cl, vp, vp, vp, vp, vp, ci]
     L.socp_fdjac_batch.argtypes = [vp, sp, cl, vp, vp, vp, vp, cd, vp, ci]

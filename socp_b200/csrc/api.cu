@@ -3,6 +3,7 @@
 // context stream, statistics.  All arithmetic of the hot path lives in the kernels.
 #include <cuda_runtime.h>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <cmath>
 #include <string>
@@ -189,8 +190,8 @@ int socp_create(int device, socp_ctx **out) {
     cudaDeviceProp prop;
     cudaGetDeviceProperties(&prop, device);
     ctx->sm_count = prop.multiProcessorCount;
-    cudaMalloc(&ctx->d_counters, 8 * sizeof(unsigned long long));
-    cudaMemset(ctx->d_counters, 0, 8 * sizeof(unsigned long long));
+    cudaMalloc(&ctx->d_counters, 64 * sizeof(unsigned long long));
+    cudaMemset(ctx->d_counters, 0, 64 * sizeof(unsigned long long));
     cudaEventCreate(&ctx->ev0);
     cudaEventCreate(&ctx->ev1);
     int zero = 0;
@@ -233,7 +234,7 @@ int socp_sync(socp_ctx *ctx) {
 
 int socp_get_stats(socp_ctx *ctx, socp_stats *out) {
     if (!ctx || !out) return SOCP_ERR_ARG;
-    unsigned long long c[8];
+    unsigned long long c[64];
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     CUDA_TRY(ctx, cudaMemcpy(c, ctx->d_counters, sizeof c, cudaMemcpyDeviceToHost));
     out->rk4_steps = (double)c[0];
@@ -248,12 +249,19 @@ int socp_get_stats(socp_ctx *ctx, socp_stats *out) {
     out->jac_ms = ctx->jac_ms;
     out->iterations = (double)c[1];
     out->jac_evals = (double)c[2];
+    if (getenv("SOCP_PHASE_CLOCKS")) {
+        fprintf(stderr, "phase clocks (cycles): res");
+        for (int k = 0; k < 8; ++k) fprintf(stderr, " %llu", c[16 + k]);
+        fprintf(stderr, " | jac");
+        for (int k = 0; k < 8; ++k) fprintf(stderr, " %llu", c[32 + k]);
+        fprintf(stderr, " | iterations %llu jac_evals %llu\n", c[1], c[2]);
+    }
     return SOCP_OK;
 }
 
 int socp_reset_stats(socp_ctx *ctx) {
     if (!ctx) return SOCP_ERR_ARG;
-    CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_counters, 0, 64 * sizeof(unsigned long long), ctx->stream));
     ctx->launches = 0;
     ctx->rounds = 0;
     ctx->integrate_ms = ctx->integrate_launches = ctx->advance_ms = ctx->advance_launches = ctx->assemble_ms = ctx->jac_ms = 0;

@@ -54,45 +54,67 @@ struct SolverDev {
     // work lists, double buffered: list[2][2][B], count[2][2]
     int *lists;
     int *counts;
-    unsigned long long *counters;
+    unsigned long long *counters;      // [0] RK4 steps, [1] Broyden iterations, [2] Jacobian factorisations, [16+k] / [32+k] phase clocks
+    int phase_clocks;                  // debugging aid (SOCP_PHASE_CLOCKS=1): accumulate clock64() per phase
 };
 
 #define EPSMCH DBL_EPSILON
 
+// phase timing of the Powell-hybrid kernels (debugging aid, off unless SolverDev::phase_clocks)
+#define SOCP_PHASE(base, k)                                                                   \
+    do {                                                                                      \
+        if (D.phase_clocks && (threadIdx.x % G) == 0) {                                       \
+            const long long now_ = clock64();                                                 \
+            atomicAdd(D.counters + (base) + (k), (unsigned long long)(now_ - phase_t0));      \
+            phase_t0 = now_;                                                                  \
+        }                                                                                     \
+    } while (0)
+
 // ---- group helpers ---------------------------------------------------------------------------
 template <int G> SOCP_DEV void gsync() { if (G == 32) __syncwarp(); else __syncthreads(); }
 
-// sum over the group; the result is identical in every thread (fixed reduction tree)
-template <int G> SOCP_DEV double gsum(double v, double *red) {
+SOCP_DEV double warp_sum_d(double v) {
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-    if (G == 32) return v;
-    const int w = threadIdx.x >> 5;
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) red[w] = v;
-    __syncthreads();
-    double t = 0;
+    return v;
+}
+SOCP_DEV double warp_max_d(double v) {
 #pragma unroll
-    for (int k = 0; k < G / 32; ++k) t += red[k];
-    return t;
+    for (int off = 16; off > 0; off >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, off));
+    return v;
 }
 
-// MINPACK enorm, sequential (used for the rare badly-scaled case)
-__device__ __noinline__ double enorm_seq(int n, const double *x, int stride) {
+// MINPACK enorm on one warp: x[0..n) (stride 1, visible to the whole warp).  Components in the
+// intermediate range are summed as plain squares; small (<= rdwarf) and large (>= rgiant/n) ones are
+// scaled by their maximum as MINPACK does, but with the maximum found first (a reduction) instead
+// of by running rescaling, so nothing is sequential.  Every lane returns the same value.
+SOCP_DEV double enorm_warp(int n, const double *x) {
     const double rdwarf = 3.834e-20, rgiant = 1.304e19;
-    double s1 = 0., s2 = 0., s3 = 0., x1max = 0., x3max = 0.;
     const double agiant = rgiant / (double)n;
-    for (int i = 0; i < n; ++i) {
-        double xabs = fabs(x[(long)i * stride]);
-        if (xabs > rdwarf && xabs < agiant) s2 += xabs * xabs;
-        else if (xabs <= rdwarf) {
-            if (xabs > x3max) { double q = x3max / xabs; s3 = 1. + s3 * (q * q); x3max = xabs; }
-            else if (xabs != 0.) { double q = xabs / x3max; s3 += q * q; }
-        } else {
-            if (xabs > x1max) { double q = x1max / xabs; s1 = 1. + s1 * (q * q); x1max = xabs; }
-            else { double q = xabs / x1max; s1 += q * q; }
-        }
+    const int lane = threadIdx.x & 31;
+    double s2 = 0., small_max = 0., big_max = 0.;
+    bool isnan_ = false;
+    for (int i = lane; i < n; i += 32) {
+        const double xabs = fabs(x[i]);
+        if (xabs > rdwarf && xabs < agiant) s2 = fma(xabs, xabs, s2);
+        else if (xabs <= rdwarf) small_max = fmax(small_max, xabs);
+        else if (xabs == xabs) big_max = fmax(big_max, xabs);
+        else isnan_ = true;
     }
+    s2 = warp_sum_d(s2);
+    if (__any_sync(0xffffffffu, isnan_)) return s2 + nan("");      // MINPACK's enorm propagates a NaN
+    const bool special = __any_sync(0xffffffffu, small_max != 0. || big_max != 0.);
+    if (!special) return sqrt(s2);
+    const double x1max = warp_max_d(big_max), x3max = warp_max_d(small_max);
+    double s1 = 0., s3 = 0.;
+    for (int i = lane; i < n; i += 32) {
+        const double xabs = fabs(x[i]);
+        if (xabs > rdwarf && xabs < agiant) continue;
+        if (xabs <= rdwarf) { if (xabs != 0.) { const double q = xabs / x3max; s3 = fma(q, q, s3); } }
+        else { const double q = xabs / x1max; s1 = fma(q, q, s1); }
+    }
+    s1 = warp_sum_d(s1);
+    s3 = warp_sum_d(s3);
     if (s1 != 0.) return x1max * sqrt(s1 + (s2 / x1max) / x1max);
     if (s2 != 0.) {
         if (s2 >= x3max) return sqrt(s2 * (1. + (x3max / s2) * (x3max * s3)));
@@ -101,22 +123,11 @@ __device__ __noinline__ double enorm_seq(int n, const double *x, int stride) {
     return x3max * sqrt(s3);
 }
 
-// Euclidean norm of x[0..n) over the group: plain sum of squares when every component is in
-// MINPACK's "intermediate" range (the normal case), the scaled sequential algorithm otherwise.
-template <int G> SOCP_DEV double enorm_g(int n, const double *x, double *red) {
-    const double rdwarf = 3.834e-20, rgiant = 1.304e19;
-    const double agiant = rgiant / (double)n;
-    const int tid = threadIdx.x % G;
-    double s2 = 0., odd = 0.;
-    for (int i = tid; i < n; i += G) {
-        double xabs = fabs(x[i]);
-        if (xabs > rdwarf && xabs < agiant) s2 += xabs * xabs;
-        else if (xabs != 0.) odd += 1.;
-    }
-    s2 = gsum<G>(s2, red);
-    odd = gsum<G>(odd, red);
-    if (odd != 0. || !(s2 == s2)) return enorm_seq(n, x, 1);
-    return sqrt(s2);
+// Euclidean norm over a thread group: every warp of the group evaluates enorm_warp on the whole
+// vector (n is a few hundred at most), so no block-level reduction or barrier is needed and every
+// thread gets the same bits.  The caller guarantees x is visible (a barrier after its last write).
+template <int G> SOCP_DEV double enorm_g(int n, const double *x, double *) {
+    return enorm_warp(n, x);
 }
 
 // ---- time line (shooting.cpp:1579-1617) --------------------------------------------------------
@@ -397,22 +408,28 @@ SOCP_DEV double warp_sum(double v) {
 
 SOCP_DEV int rowstart(int n, int j) { return j * n - (j * (j - 1)) / 2; }
 
+// dot product with four independent accumulators (the 8-cycle DFMA latency would otherwise pace a
+// single running sum); fixed summation tree, so the result is deterministic
+SOCP_DEV double dot4(const double *a, const double *b, int m) {
+    double s0 = 0., s1 = 0., s2 = 0., s3 = 0.;
+    int i = 0;
+    for (; i + 3 < m; i += 4) {
+        s0 = fma(a[i], b[i], s0); s1 = fma(a[i + 1], b[i + 1], s1);
+        s2 = fma(a[i + 2], b[i + 2], s2); s3 = fma(a[i + 3], b[i + 3], s3);
+    }
+    for (; i < m; ++i) s0 = fma(a[i], b[i], s0);
+    return (s0 + s1) + (s2 + s3);
+}
+
 // qrfac (no pivoting) fused with "qtf = Q^T fvec" (the Householder reflections are applied to
 // qtf as one more column); rdiag/acnorm as in MINPACK.  One thread per column.
 template <int G>
 __device__ void qrfac_g(int n, double *a, int lda, double *rdiag, double *acnorm, double *qtf, double *red) {
     const int tid = threadIdx.x % G;
     gsync<G>();
-    for (int j = tid; j < n; j += G) {                 // column norms
-        const double *cj = a + (size_t)j * lda;
-        double s2 = 0;
-        bool odd = false;
-        for (int i = 0; i < n; ++i) {
-            double v = fabs(cj[i]);
-            if (v > 3.834e-20 && v < 1.304e19 / n) s2 += v * v;
-            else if (v != 0.) odd = true;
-        }
-        acnorm[j] = odd ? enorm_seq(n, cj, 1) : sqrt(s2);
+    for (int j = tid >> 5; j < n; j += G / 32) {       // column norms, one warp per column
+        const double v = enorm_warp(n, a + (size_t)j * lda);
+        if ((tid & 31) == 0) acnorm[j] = v;
     }
     gsync<G>();
     for (int j = 0; j < n; ++j) {
@@ -430,8 +447,7 @@ __device__ void qrfac_g(int n, double *a, int lda, double *rdiag, double *acnorm
             const double ajj = cj[j];
             for (int k = j + 1 + tid; k <= n; k += G) {  // remaining columns, and qtf as column n
                 double *ck = (k < n) ? a + (size_t)k * lda : qtf;
-                double sum = 0.;
-                for (int i = j; i < n; ++i) sum += cj[i] * ck[i];
+                const double sum = dot4(cj + j, ck + j, n - j);
                 const double temp = sum / ajj;
                 for (int i = j; i < n; ++i) ck[i] -= temp * cj[i];
             }
@@ -469,8 +485,7 @@ __device__ void qform_g(int n, double *q, int lda, double *wa) {
         if (wk != 0.) {
             for (int j = k + tid; j < n; j += G) {
                 double *cj = q + (size_t)j * lda;
-                double sum = 0.;
-                for (int i = k; i < n; ++i) sum += cj[i] * wa[i];
+                const double sum = dot4(cj + k, wa + k, n - k);
                 const double temp = sum / wk;
                 for (int i = k; i < n; ++i) cj[i] -= temp * wa[i];
             }
@@ -855,6 +870,7 @@ hybrd_res_kernel(SolverDev D, int cur, int per_group_doubles) {
             continue;
         }
         // ---- trial point evaluated: wa4 = F(x + p) ----
+        long long phase_t0 = clock64();
         Work W;
         W.x = vec; W.xe = vec + n; W.fvec = vec + 2 * n; W.diag = vec + 3 * n; W.qtf = vec + 4 * n;
         W.wa1 = vec + 5 * n; W.wa4 = vec + 6 * n; W.wa2 = vec + 7 * n; W.wa3 = vec + 8 * n; W.scr = vec + 9 * n;
@@ -866,6 +882,7 @@ hybrd_res_kernel(SolverDev D, int cur, int per_group_doubles) {
         gcopy<G>(W.wa4, D.wa4 + b * n, n);
         if (STAGE_R) gcopy<G>(W.r, D.r + (size_t)b * D.LR, D.LR);
         gsync<G>();
+        SOCP_PHASE(16, 0);
 
         const double fnorm1 = enorm_g<G>(n, W.wa4, red);
         double fnorm = ds[D_FNORM], delta = ds[D_DELTA], xnorm = ds[D_XNORM];
@@ -892,6 +909,7 @@ hybrd_res_kernel(SolverDev D, int cur, int per_group_doubles) {
         }
         int base = is[I_BASE];
         gsync<G>();
+        SOCP_PHASE(16, 1);
         if (ratio >= p0001) {
             // successful iteration: x <- x + p, fvec <- wa4
             for (int j = tid; j < n; j += G) {
@@ -937,6 +955,7 @@ hybrd_res_kernel(SolverDev D, int cur, int per_group_doubles) {
         } else {
             // rank-one (Broyden) update of the QR factors: sum_j = Q(:,j) . wa4, one warp per
             // column, four columns in flight so that the HBM/L2 loads of Q overlap
+            SOCP_PHASE(16, 2);
             {
                 const int lane = threadIdx.x & 31, warp = tid >> 5;
                 constexpr int NW = G / 32;
@@ -963,19 +982,25 @@ hybrd_res_kernel(SolverDev D, int cur, int per_group_doubles) {
                 }
             }
             if (tid == 0) atomicAdd(D.counters + 1, 1ULL);
+            gsync<G>();
+            SOCP_PHASE(16, 3);
             r1updt_g<G>(n, W.r, W.wa1, W.wa2, W.wa3, W.scr, W.scr + n, W.scr + 2 * n);
+            SOCP_PHASE(16, 4);
             r1coef_g<G>(n, W.wa2, W.wa3, W.scr);
             r1mpyq_g<G>(n, n, W.q, W.ldq, W.scr);
             r1mpyq_g<G>(1, n, W.qtf, 1, W.scr);
+            SOCP_PHASE(16, 5);
             if (tid == 0) is[I_JEVAL] = 0;
             dogleg_and_request<G>(D, b, W, is, ds, red, next_res, next_cnt);
             store_r = true;
+            SOCP_PHASE(16, 6);
         }
         gsync<G>();
         gcopy<G>(D.x + b * n, W.x, n); gcopy<G>(D.xe + b * n, W.xe, n); gcopy<G>(D.fvec + b * n, W.fvec, n);
         gcopy<G>(D.qtf + b * n, W.qtf, n); gcopy<G>(D.wa1 + b * n, W.wa1, n);
         if (STAGE_R && store_r) gcopy<G>(D.r + (size_t)b * D.LR, W.r, D.LR);
         gsync<G>();
+        SOCP_PHASE(16, 7);
     }
 }
 
@@ -1014,14 +1039,18 @@ hybrd_jac_kernel(SolverDev D, int cur, int per_group_doubles) {
         double *gq = D.fjac + (size_t)b * n * n;
         W.q = STAGE_Q ? after : gq;
         W.ldq = STAGE_Q ? ldq_s : n;
+        long long phase_t0 = clock64();
         gcopy<G>(W.x, D.x + b * n, n); gcopy<G>(W.fvec, D.fvec + b * n, n); gcopy<G>(W.diag, D.diag + b * n, n);
         if (STAGE_Q)
-            for (int e = tid; e < n * n; e += G) W.q[(e % n) + (size_t)(e / n) * ldq_s] = gq[e];
+            for (int c = tid >> 5; c < n; c += G / 32)
+                for (int i = tid & 31; i < n; i += 32) W.q[i + (size_t)c * ldq_s] = gq[i + (size_t)c * n];
         gsync<G>();
+        SOCP_PHASE(32, 0);
         if (tid == 0) { is[I_NFEV] += n; is[I_JEVAL] = 1; atomicAdd(D.counters + 2, 1ULL); }
         for (int i = tid; i < n; i += G) W.qtf[i] = W.fvec[i];
         // wa1 = rdiag, wa2 = acnorm
         qrfac_g<G>(n, W.q, W.ldq, W.wa1, W.wa2, W.qtf, red);
+        SOCP_PHASE(32, 1);
         if (is[I_ITER] == 1) {
             for (int j = tid; j < n; j += G) {
                 double dj = W.wa2[j];
@@ -1037,7 +1066,9 @@ hybrd_jac_kernel(SolverDev D, int cur, int per_group_doubles) {
             if (tid == 0) { ds[D_XNORM] = xnorm; ds[D_DELTA] = delta; }
         }
         pack_r_g<G>(n, W.q, W.ldq, W.wa1, W.r);
+        SOCP_PHASE(32, 2);
         qform_g<G>(n, W.q, W.ldq, W.wa1);
+        SOCP_PHASE(32, 3);
         for (int j = tid; j < n; j += G) W.diag[j] = fmax(W.diag[j], W.wa2[j]);
         gsync<G>();
         dogleg_and_request<G>(D, b, W, is, ds, red, next_res, next_cnt);
@@ -1045,9 +1076,12 @@ hybrd_jac_kernel(SolverDev D, int cur, int per_group_doubles) {
         gcopy<G>(D.xe + b * n, W.xe, n); gcopy<G>(D.diag + b * n, W.diag, n);
         gcopy<G>(D.qtf + b * n, W.qtf, n); gcopy<G>(D.wa1 + b * n, W.wa1, n);
         if (STAGE_R) gcopy<G>(D.r + (size_t)b * D.LR, W.r, D.LR);
+        SOCP_PHASE(32, 5);
         if (STAGE_Q)
-            for (int e = tid; e < n * n; e += G) gq[e] = W.q[(e % n) + (size_t)(e / n) * ldq_s];
+            for (int c = tid >> 5; c < n; c += G / 32)
+                for (int i = tid & 31; i < n; i += 32) gq[i + (size_t)c * n] = W.q[i + (size_t)c * ldq_s];
         gsync<G>();
+        SOCP_PHASE(32, 6);
     }
 }
 

@@ -107,7 +107,7 @@ cudaEvent_t prof_event(socp_ctx *ctx, int idx) {
 }
 
 // accumulate the per-kernel times of the last `n` profiled rounds (events must have completed)
-void prof_harvest(socp_ctx *ctx, int n) {
+void prof_harvest(socp_ctx *ctx, int n, FILE *log = nullptr, long round0 = 0, const int *counts = nullptr) {
     for (int k = 0; k < n; ++k) {
         float a = 0, b = 0, c = 0, d = 0;
         cudaEventElapsedTime(&a, ctx->prof_events[kProfEv * k], ctx->prof_events[kProfEv * k + 1]);
@@ -118,6 +118,7 @@ void prof_harvest(socp_ctx *ctx, int n) {
         cudaEventElapsedTime(&d, ctx->prof_events[kProfEv * k + 3], ctx->prof_events[kProfEv * k + 4]);
         ctx->advance_ms += c + d; ctx->advance_launches += 2;
         ctx->jac_ms += d;
+        if (log) fprintf(log, "%ld %d %d %.4f %.4f %.4f %.4f\n", round0 + k, counts ? counts[0] : -1, counts ? counts[1] : -1, a, b, c, d);
     }
 }
 
@@ -130,9 +131,10 @@ struct SmemPlan {
     size_t bytes_res, bytes_jac;         // per CTA
 };
 
-// One warp per problem up to P = 32, a 128-thread CTA above (measured: at P = 85 the CTA variant
-// is 13% faster than one warp per problem).  R and the work vectors live in shared memory when
-// they fit, Q too in the Jacobian phase.
+// One warp per problem up to P = 32, a 128-thread CTA above (measured at P = 85: one warp per problem
+// with R left in global memory is within 13% of the CTA variant, a register-resident Householder QR
+// was 1.7x slower than the shared-memory one -- see DESIGN.md section 7).  R and the work vectors
+// live in shared memory when they fit, Q too in the Jacobian phase.
 SmemPlan smem_plan(const SolverDev &D) {
     const size_t limit = 225 * 1024;
     const size_t base = 8 + 13 * (size_t)D.P;
@@ -253,9 +255,14 @@ int run_solver(socp_ctx *ctx, const socp_shape *shape, long B, const double *d_m
     }
     D.xtol = xtol; D.epsfcn = epsfcn; D.factor = 1.0; D.maxfev = maxfev; D.run_mode = run_mode;
     D.counters = ctx->d_counters;
+    D.phase_clocks = getenv("SOCP_PHASE_CLOCKS") ? 1 : 0;
     const int grid_int = ctx->sm_count * 8;
     const int grid_adv = ctx->sm_count * 6;
-    const int check_every = (run_mode == RUN_SOLVE) ? 8 : 1;   // <= kProfSlots
+    // debugging aid: SOCP_ROUND_LOG=<file> (with profiling on) logs every round: index, residual and
+    // Jacobian requests entering it, and the CUDA-event time of its four kernels (ms)
+    const char *round_log_path = ctx->profile ? getenv("SOCP_ROUND_LOG") : nullptr;
+    FILE *round_log = round_log_path ? fopen(round_log_path, "a") : nullptr;
+    const int check_every = (run_mode == RUN_SOLVE && !round_log) ? 8 : 1;   // <= kProfSlots
     const long max_rounds = (run_mode == RUN_SOLVE) ? (long)maxfev + 8 : (run_mode == RUN_FDJAC ? 2 : 1);
 
     for (long first = 0; first < B; first += wave) {
@@ -268,6 +275,7 @@ int run_solver(socp_ctx *ctx, const socp_shape *shape, long B, const double *d_m
         solver_init<<<(unsigned)((nthreads + 255) / 256), 256, 0, ctx->stream>>>(D, d_x_in, first);
         ctx->launches += 1;
         int cur = 0, pending = 0;
+        int entering[2] = {(int)Bw, 0};
         for (long round = 0; round < max_rounds; ++round) {
             launch_round_any(ctx, D, cur, grid_int, grid_adv, ctx->profile ? pending : -1);
             ++pending;
@@ -276,8 +284,9 @@ int run_solver(socp_ctx *ctx, const socp_shape *shape, long B, const double *d_m
                 CUDA_TRY(ctx, cudaMemcpyAsync(ctx->solver.h_counts, D.counts, 4 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
                 CUDA_TRY(ctx, cudaEventRecord(ctx->solver.ev, ctx->stream));
                 CUDA_TRY(ctx, cudaEventSynchronize(ctx->solver.ev));
-                if (ctx->profile) prof_harvest(ctx, pending);
+                if (ctx->profile) prof_harvest(ctx, pending, round_log, round, entering);
                 pending = 0;
+                entering[0] = ctx->solver.h_counts[cur * 2]; entering[1] = ctx->solver.h_counts[cur * 2 + 1];
                 if (ctx->solver.h_counts[cur * 2] + ctx->solver.h_counts[cur * 2 + 1] == 0) break;
             }
         }
@@ -290,6 +299,7 @@ int run_solver(socp_ctx *ctx, const socp_shape *shape, long B, const double *d_m
         ctx->launches += 1;
         CUDA_TRY(ctx, cudaGetLastError());
     }
+    if (round_log) fclose(round_log);
     return SOCP_OK;
 }
 

@@ -205,6 +205,22 @@ class Engine:
                                             a.inp(t0), a.inp(tf), a.inp(X0), a.out(out), mem))
         return out
 
+    def trace_batch(self, model_id, mparams, t0, X0, tf, step_nbr=0, sw=None):
+        """The observer form of ComputeTraj (socp_trace_batch): rows[B][R][W] = {t, X, control, H, extra}
+        as model::Trace writes them (model.hpp:446-462), nrows[B], Xf[B][N].  Host arrays."""
+        X0 = np.ascontiguousarray(X0, dtype=np.float64)
+        B, N = X0.shape
+        mparams = self._bcast_params(mparams, B, model_nparams(model_id))
+        t0 = np.broadcast_to(np.asarray(t0, dtype=np.float64), (B,))
+        tf = np.broadcast_to(np.asarray(tf, dtype=np.float64), (B,))
+        W = self._L.socp_trace_width(model_id)
+        R = self._L.socp_trace_max_rows(model_id, int(step_nbr or 0))
+        rows, nrows, Xf = np.zeros((B, R, W)), np.zeros(B, dtype=np.int32), np.empty((B, N))
+        a = _Arg(HOST)
+        self._check(self._L.socp_trace_batch(self._h, model_id, int(step_nbr or 0), B, a.inp(mparams), a.inp(sw),
+                                             a.inp(t0), a.inp(tf), a.inp(X0), a.out(rows), a.out(nrows), a.out(Xf), HOST))
+        return rows, nrows, Xf
+
     def point_batch(self, model_id, mparams, t, X, sw=None, chart_stage=None):
         """odeTools::Model, model::Control, model::Hamiltonian at B points (host arrays)."""
         X = np.ascontiguousarray(X, dtype=np.float64)
