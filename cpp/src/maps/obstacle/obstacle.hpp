@@ -31,6 +31,8 @@ public:
 	int Count() const;
 	/// obstacle table as {type[n], pos[n][3], rad[n][3]} for socp_set_obstacles
 	void Table(std::vector<real> & type, std::vector<real> & pos, std::vector<real> & rad) const;
+	/// push the table to the engine context (socp_set_obstacles); done lazily, once
+	void Upload() const;
 
 private:
 	struct data_struct;

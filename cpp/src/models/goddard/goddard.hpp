@@ -32,7 +32,7 @@ public:
 
 	virtual int DeviceModelId() const;
 	virtual std::vector<real> DeviceParams() const;
-	virtual void TraceExtra(real const& t, mstate const& X, std::ostream & file) const;
+	virtual void TraceTail(real H, real extra, std::ostream & file) const;
 };
 
 #endif //_GODDARD_H_

@@ -39,11 +39,16 @@ public:
 	parameters_struct & GetParameterData();
 	void InitAnalytical(real const& ti, mstate & Xi, real const& tf, mstate & Xf) const;
 
+	virtual mstate ComputeTraj(real const& t0, mstate const& X0, real const& tf, int isTrace, int isJac);
+	virtual int GetMode(real const& t, mstate const& X) const;
+
 	virtual int DeviceModelId() const;
 	virtual std::vector<real> DeviceParams() const;
 	virtual int DeviceSteps() const { return 50; }		///< interceptor.cpp:54 (per stage)
+	virtual void TraceTail(real H, real extra, std::ostream & file) const;
 
 private:
+	real ComputeMass(real const& t, mstate const& X) const;
 	struct data_struct;
 	data_struct *data;
 };

@@ -71,8 +71,9 @@ public:
 	virtual int DeviceSteps() const { return stepNbr; }
 	/// switching times pushed by shooting::ComputeTimeLine (goddard.cpp:373)
 	std::vector<real> deviceSwitchingTimes;
-	/// extra columns a model appends to a trace row (goddard: switching function; interceptor: chart)
-	virtual void TraceExtra(real const& t, mstate const& X, std::ostream & file) const {}
+	/// end of a trace row: H, then whatever the model appends (goddard: switching function,
+	/// goddard.cpp:337; interceptor: chart id, interceptor.cpp:151); `extra` is the device's last column
+	virtual void TraceTail(real H, real extra, std::ostream & file) const;
 	static socp_ctx* Context();					///< process-wide engine context (device 0 or $SOCP_DEVICE)
 
 private:
