@@ -27,7 +27,7 @@ socp_ctx *model::Context() {
 }
 
 model::model(int const& _stateDim, int _modelOrder, int _stepNbr, std::string _fileTrace)
-	: dim(_stateDim), modelOrder(_modelOrder), strFileTrace(_fileTrace), stepNbr(_stepNbr) {
+	: dim(_stateDim), modelOrder(_modelOrder), strFileTrace(_fileTrace), stepNbr(_stepNbr), deviceAdaptive(0) {
 	// the reference truncates the trace file in the constructor (model.hpp:51-54)
 	std::ofstream fileTrace;
 	fileTrace.open(strFileTrace.c_str(), std::ios::trunc);
@@ -93,6 +93,10 @@ model::mstate model::ModelInt(real const& t0, mstate const& X, real const& tf, i
 		fileTrace.open(strFileTrace.c_str(), std::ios::app);
 		fileTrace << ss.str();
 		fileTrace.close();
+	} else if (deviceAdaptive) {
+		if (socp_traj_adaptive_batch(dc.ctx, dc.id, DeviceSteps(), 1, dc.mp.data(), dc.sw, &t0, &tf, Xin.data(), odeIntTol,
+		                             Xout.data(), nullptr, SOCP_HOST) != SOCP_OK)
+			die("socp_traj_adaptive_batch", dc.ctx);
 	} else {
 		if (socp_traj_batch(dc.ctx, dc.id, DeviceSteps(), 1, dc.mp.data(), dc.sw, &t0, &tf, Xin.data(), Xout.data(), SOCP_HOST) != SOCP_OK)
 			die("socp_traj_batch", dc.ctx);

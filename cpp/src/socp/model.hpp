@@ -69,6 +69,10 @@ public:
 	virtual std::vector<real> DeviceParams() const { return std::vector<real>(); }
 	/// RK4 steps per segment the device should use (the model's own stepNbr)
 	virtual int DeviceSteps() const { return stepNbr; }
+	/// 0 (default): fixed-step RK4, the reference's default build; 1: adaptive Dormand-Prince with
+	/// abs = rel = odeIntTol, the reference's -D_USE_BOOST build (odeTools.cpp:131-134)
+	int deviceAdaptive;
+	void SetAdaptiveIntegration(bool on) { deviceAdaptive = on ? 1 : 0; }
 	/// switching times pushed by shooting::ComputeTimeLine (goddard.cpp:373)
 	std::vector<real> deviceSwitchingTimes;
 	/// end of a trace row: H, then whatever the model appends (goddard: switching function,

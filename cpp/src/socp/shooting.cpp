@@ -301,8 +301,10 @@ int shooting::SolveShootingFunction(int const & numParam, std::vector<real> & pa
 		std::cerr << std::endl << "ERROR : this model has no device implementation; the B200 engine has no CPU fallback" << std::endl;
 		exit(1);
 	}
-	socp_shape shape;
+	socp_shape shape = socp_shape();
 	shape.model_id = myModel.DeviceModelId();
+	shape.integrator = myModel.deviceAdaptive ? SOCP_DOPRI5 : SOCP_RK4;
+	shape.ode_tol = myModel.odeIntTol;
 	shape.num_multi = data->numMulti;
 	shape.step_nbr = myModel.DeviceSteps();
 	for (int j = 0; j <= data->numMulti; j++) {

@@ -44,6 +44,8 @@ shooting_batch::shooting_batch(model & model, int numMulti, long batch) : myMode
 	data->shape.model_id = model.DeviceModelId();
 	data->shape.num_multi = numMulti;
 	data->shape.step_nbr = model.DeviceSteps();
+	data->shape.integrator = model.deviceAdaptive ? SOCP_DOPRI5 : SOCP_RK4;
+	data->shape.ode_tol = model.odeIntTol;
 	const std::vector<real> block = model.DeviceParams();
 	data->np = (int)block.size();
 	data->mparams.resize((size_t)batch * data->np);

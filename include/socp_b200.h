@@ -37,6 +37,9 @@ enum { SOCP_GODDARD = 0, SOCP_DOUBLE_INTEGRATOR = 1, SOCP_COVID19 = 2, SOCP_VTOL
 /* model::FIXED / FREE / CONTINUOUS (src/socp/model.hpp:34-38) */
 enum { SOCP_FIXED = 0, SOCP_FREE = 1, SOCP_CONTINUOUS = 2 };
 enum { SOCP_HOST = 0, SOCP_DEVICE = 1 };
+/* integrator of model::ModelInt: fixed-step RK4 (the reference's default build, odeTools.cpp:135-144)
+ * or adaptive Dormand-Prince 5(4) (its -D_USE_BOOST build, odeTools.cpp:131-134) */
+enum { SOCP_RK4 = 0, SOCP_DOPRI5 = 1 };
 enum { SOCP_OK = 0, SOCP_ERR_ARG = -1, SOCP_ERR_CUDA = -2, SOCP_ERR_NOMEM = -3, SOCP_ERR_UNSUPPORTED = -4 };
 
 #define SOCP_MAX_NODES 64
@@ -62,6 +65,8 @@ typedef struct {
     int step_nbr;
     int mode_t[SOCP_MAX_NODES];
     int mode_X[SOCP_MAX_NODES][SOCP_MAX_DIM];
+    int integrator;          /* SOCP_RK4 (0, default) or SOCP_DOPRI5 */
+    double ode_tol;          /* SOCP_DOPRI5: absolute = relative tolerance (odeTools::odeIntTol, odeTools.hpp:62) */
 } socp_shape;
 
 typedef struct {
@@ -77,6 +82,7 @@ typedef struct {
     double jac_ms;                             /* hybrd_jac_kernel alone (included in advance_ms) */
     double iterations;                         /* problem-iterations of hybrd_res_kernel (Broyden steps), device counter */
     double jac_evals;                          /* Jacobian factorisations of hybrd_jac_kernel, device counter */
+    double dopri_steps;                        /* accepted Dormand-Prince steps of the adaptive integration kernels */
 } socp_stats;
 
 /* ---- context ------------------------------------------------------------------------------ */
@@ -112,6 +118,14 @@ int socp_set_obstacles(socp_ctx *ctx, int n, const double *type, const double *p
 int socp_traj_batch(socp_ctx *ctx, int model_id, int step_nbr, long B, const double *mparams,
                     const double *sw, const double *t0, const double *tf, const double *X0,
                     double *Xf, int mem);
+
+/* The same with the adaptive integrator of the reference's -D_USE_BOOST build (odeTools.cpp:131-134):
+ * Boost.Odeint integrate_adaptive with a dense-output Dormand-Prince 5(4) stepper, abs = rel = tol, first
+ * trial step (tf - t0) / step_nbr.  nsteps: optional [B][2] = {accepted steps, rejected attempts}.
+ * The interceptor integrates with its own fixed-step loop in that build too (interceptor.cpp:104-130). */
+int socp_traj_adaptive_batch(socp_ctx *ctx, int model_id, int step_nbr, long B, const double *mparams,
+                             const double *sw, const double *t0, const double *tf, const double *X0,
+                             double tol, double *Xf, int *nsteps, int mem);
 
 /* The observer form of the same integration (odeTools.cpp:103-123 with model::Trace,
  * model.hpp:446-462; shooting::Trace re-integrates every segment this way, shooting.cpp:496-544):

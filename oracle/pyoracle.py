@@ -34,7 +34,9 @@ class Problem(ctypes.Structure):
                 ("obs", ctypes.POINTER(Obstacles)),
                 ("sw", ctypes.c_double * MAX_NODES), ("nsw", ctypes.c_int),
                 ("chart", ctypes.c_int), ("stage", ctypes.c_int), ("rk4_steps", ctypes.c_long),
-                ("noise_ulps", ctypes.c_double), ("noise_state", ctypes.c_ulonglong)]
+                ("noise_ulps", ctypes.c_double), ("noise_state", ctypes.c_ulonglong),
+                ("integrator", ctypes.c_int), ("ode_tol", ctypes.c_double),
+                ("dopri_steps", ctypes.c_long), ("dopri_rejected", ctypes.c_long)]
 
 
 _SIGS = False

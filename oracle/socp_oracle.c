@@ -865,6 +865,98 @@ void so_integrate(so_problem *p, double *X, double t0, double tf, double dt)
     }
 }
 
+/* ---- adaptive Dormand-Prince 5(4), the reference's -D_USE_BOOST build -----------------------------
+ * odeTools.cpp:131-134 calls
+ *     boost::numeric::odeint::integrate_adaptive(
+ *         make_dense_output<runge_kutta_dopri5<odeVector>>(odeIntTol, odeIntTol), model, X, t0, tf, dt)
+ * Boost.Odeint is a third-party dependency that is neither vendored in the reference nor present in
+ * this container (unpinned system package, CMakeLists.txt:72-79), so this is a restatement of its
+ * published algorithm (boost/numeric/odeint 1.7x: stepper/runge_kutta_dopri5.hpp,
+ * stepper/controlled_runge_kutta.hpp, stepper/dense_output_runge_kutta.hpp,
+ * integrate/detail/integrate_adaptive.hpp) and PARITY IS UNPINNED against the real library:
+ *   - stages and operation order of runge_kutta_dopri5::do_step_impl (coefficients pre-multiplied by
+ *     dt, sums left to right), FSAL derivative, error estimate with the dc coefficients;
+ *   - default_error_checker: max_i |xerr_i| / (eps_abs + eps_rel (|x_i| + |dt| |dxdt_i|)) on the state
+ *     and derivative at the START of the step;
+ *   - default_step_adjuster: reject if err > 1 and dt *= max(0.9 err^(-1/3), 1/5); accept otherwise and,
+ *     if err < 0.5, dt *= 0.9 max(err, 5^-5)^(-1/5);
+ *   - integrate_adaptive for dense-output steppers: whole steps while t + dt <= tf (with Boost's
+ *     epsilon-guarded comparisons), then the step is clamped to land on tf, until tf - t <= epsilon. */
+static void dopri5_try(so_problem *p, double t, const double *in, const double *k1, double dt,
+                       double *out, double *k7, double *xerr)
+{
+    const int N = 2 * p->dim;
+    const double a2 = 1.0 / 5, a3 = 3.0 / 10, a4 = 4.0 / 5, a5 = 8.0 / 9;
+    const double b21 = 1.0 / 5, b31 = 3.0 / 40, b32 = 9.0 / 40, b41 = 44.0 / 45, b42 = -56.0 / 15, b43 = 32.0 / 9,
+                 b51 = 19372.0 / 6561, b52 = -25360.0 / 2187, b53 = 64448.0 / 6561, b54 = -212.0 / 729,
+                 b61 = 9017.0 / 3168, b62 = -355.0 / 33, b63 = 46732.0 / 5247, b64 = 49.0 / 176, b65 = -5103.0 / 18656;
+    const double c1 = 35.0 / 384, c3 = 500.0 / 1113, c4 = 125.0 / 192, c5 = -2187.0 / 6784, c6 = 11.0 / 84;
+    const double dc1 = c1 - 5179.0 / 57600, dc3 = c3 - 7571.0 / 16695, dc4 = c4 - 393.0 / 640,
+                 dc5 = c5 - (-92097.0 / 339200), dc6 = c6 - 187.0 / 2100, dc7 = -1.0 / 40;
+    double k2[SO_MAX_N], k3[SO_MAX_N], k4[SO_MAX_N], k5[SO_MAX_N], k6[SO_MAX_N], y[SO_MAX_N];
+    for (int i = 0; i < N; ++i) y[i] = 1.0 * in[i] + dt * b21 * k1[i];
+    so_rhs(p, t + dt * a2, y, k2);
+    for (int i = 0; i < N; ++i) y[i] = 1.0 * in[i] + dt * b31 * k1[i] + dt * b32 * k2[i];
+    so_rhs(p, t + dt * a3, y, k3);
+    for (int i = 0; i < N; ++i) y[i] = 1.0 * in[i] + dt * b41 * k1[i] + dt * b42 * k2[i] + dt * b43 * k3[i];
+    so_rhs(p, t + dt * a4, y, k4);
+    for (int i = 0; i < N; ++i)
+        y[i] = 1.0 * in[i] + dt * b51 * k1[i] + dt * b52 * k2[i] + dt * b53 * k3[i] + dt * b54 * k4[i];
+    so_rhs(p, t + dt * a5, y, k5);
+    for (int i = 0; i < N; ++i)
+        y[i] = 1.0 * in[i] + dt * b61 * k1[i] + dt * b62 * k2[i] + dt * b63 * k3[i] + dt * b64 * k4[i] + dt * b65 * k5[i];
+    so_rhs(p, t + dt, y, k6);
+    for (int i = 0; i < N; ++i)
+        out[i] = 1.0 * in[i] + dt * c1 * k1[i] + dt * c3 * k3[i] + dt * c4 * k4[i] + dt * c5 * k5[i] + dt * c6 * k6[i];
+    so_rhs(p, t + dt, out, k7);
+    for (int i = 0; i < N; ++i)
+        xerr[i] = dt * dc1 * k1[i] + dt * dc3 * k3[i] + dt * dc4 * k4[i] + dt * dc5 * k5[i] + dt * dc6 * k6[i] + dt * dc7 * k7[i];
+}
+
+void so_integrate_adaptive(so_problem *p, double *X, double t0, double tf, double dt, double tol)
+{
+    const int N = 2 * p->dim;
+    const double eps = 2.220446049250313e-16;
+    double t = t0, k1[SO_MAX_N], out[SO_MAX_N], k7[SO_MAX_N], xerr[SO_MAX_N];
+    int have_deriv = 0;
+    if (!(dt > 0)) return;                             /* the reference only integrates forward */
+    while (tf - t > eps) {                             /* less_with_sign(t, tf, dt) */
+        while ((t + dt) - tf <= eps) {                 /* less_eq_with_sign(t + dt, tf, dt) */
+            /* dense_output_runge_kutta::do_step: retry until the controller accepts (at most 500 times) */
+            if (!have_deriv) { so_rhs(p, t, X, k1); have_deriv = 1; }
+            int failed = 0, ok = 0;
+            while (!ok && failed < 500) {
+                dopri5_try(p, t, X, k1, dt, out, k7, xerr);
+                double err = 0;
+                for (int i = 0; i < N; ++i) {
+                    double e = fabs(xerr[i]) / (tol + tol * (1.0 * fabs(X[i]) + fabs(dt) * fabs(k1[i])));
+                    if (e > err || e != e) err = e;
+                }
+                if (err > 1.0 || err != err) {
+                    double f = 0.9 * pow(err, -1.0 / 3.0);
+                    dt *= (f > 0.2 && f == f) ? f : 0.2;
+                    ++failed;
+                    ++p->dopri_rejected;
+                } else {
+                    t += dt;
+                    if (err < 0.5) {
+                        double e5 = pow(5.0, -5.0);
+                        if (err < e5) err = e5;
+                        dt *= 0.9 * pow(err, -1.0 / 5.0);
+                    }
+                    ok = 1;
+                }
+            }
+            if (!ok) return;                           /* Boost throws step_adjustment_error here */
+            for (int i = 0; i < N; ++i) { X[i] = out[i]; k1[i] = k7[i]; }
+            ++p->dopri_steps;
+        }
+        /* st.initialize(current_state, current_time, tf - t): the derivative is evaluated again */
+        dt = tf - t;
+        have_deriv = 0;
+    }
+}
+
 /* interceptor.cpp:104-130 */
 static void icp_model_int(so_problem *p, double t0, double *X, double tf)
 {
@@ -886,7 +978,8 @@ void so_traj(so_problem *p, double t0, const double *X0, double tf, double *Xf)
     for (int i = 0; i < N; ++i) X[i] = X0[i];
     if (p->model_id != SO_INTERCEPTOR) {
         double dt = (tf - t0) / p->step_nbr;
-        so_integrate(p, X, t0, tf, dt);
+        if (p->integrator == 1) so_integrate_adaptive(p, X, t0, tf, dt, p->ode_tol);
+        else so_integrate(p, X, t0, tf, dt);
     } else {
         p->chart = 1;
         double t1 = p->mparams[I_mprop] / p->mparams[I_q];

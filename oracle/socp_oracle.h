@@ -55,6 +55,11 @@ typedef struct {
      * estimate of how far a libm / FMA difference of that many ulps can move a result */
     double noise_ulps;
     unsigned long long noise_state;
+    /* integrator of model::ModelInt: 0 = fixed-step RK4 (the reference's default build), 1 = adaptive
+     * Dormand-Prince as the reference's -D_USE_BOOST build (odeTools.cpp:131-134), abs = rel = ode_tol */
+    int integrator;
+    double ode_tol;
+    long dopri_steps, dopri_rejected;       /* statistics */
 } so_problem;
 
 void so_problem_init(so_problem *p, int model_id, int num_multi);   /* model ctor defaults */
@@ -69,6 +74,10 @@ void so_obstacle_eval(const so_problem *p, const double *pos, double *func, doub
 void so_rk4_step(so_problem *p, double t, double *X, double h);                   /* odeTools.cpp:89 */
 void so_integrate(so_problem *p, double *X, double t0, double tf, double dt);     /* odeTools.cpp:128 */
 void so_traj(so_problem *p, double t0, const double *X0, double tf, double *Xf);  /* model.hpp:77 */
+/* Boost.Odeint integrate_adaptive(make_dense_output<runge_kutta_dopri5>(tol, tol), f, X, t0, tf, dt)
+ * restated from the published Boost 1.7x sources (Boost is absent here: PARITY UNPINNED, see the
+ * function's comment in socp_oracle.c) */
+void so_integrate_adaptive(so_problem *p, double *X, double t0, double tf, double dt, double tol);
 
 void so_timeline(so_problem *p, const double *x, double *tl);                     /* shooting.cpp:1579 */
 void so_residual(so_problem *p, const double *x, double *fvec);                   /* shooting.cpp:918 */

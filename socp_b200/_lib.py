@@ -16,7 +16,8 @@ class SocpError(RuntimeError):
 
 class Shape(ctypes.Structure):
     _fields_ = [("model_id", ctypes.c_int), ("num_multi", ctypes.c_int), ("step_nbr", ctypes.c_int),
-                ("mode_t", ctypes.c_int * MAX_NODES), ("mode_X", (ctypes.c_int * MAX_DIM) * MAX_NODES)]
+                ("mode_t", ctypes.c_int * MAX_NODES), ("mode_X", (ctypes.c_int * MAX_DIM) * MAX_NODES),
+                ("integrator", ctypes.c_int), ("ode_tol", ctypes.c_double)]
 
 
 class Stats(ctypes.Structure):
@@ -25,7 +26,7 @@ class Stats(ctypes.Structure):
                 ("integrate_ms", ctypes.c_double), ("integrate_launches", ctypes.c_double),
                 ("advance_ms", ctypes.c_double), ("advance_launches", ctypes.c_double),
                 ("assemble_ms", ctypes.c_double), ("jac_ms", ctypes.c_double),
-                ("iterations", ctypes.c_double), ("jac_evals", ctypes.c_double)]
+                ("iterations", ctypes.c_double), ("jac_evals", ctypes.c_double), ("dopri_steps", ctypes.c_double)]
 
 
 _LIB = None
@@ -33,7 +34,7 @@ _LIB = None
 SYMBOLS = ["socp_create", "socp_destroy", "socp_last_error", "socp_set_stream", "socp_sync",
            "socp_get_stats", "socp_reset_stats", "socp_set_profiling", "socp_timer_start", "socp_timer_stop",
            "socp_model_dim", "socp_model_nparams", "socp_model_default_steps",
-           "socp_model_default_params", "socp_num_param", "socp_set_obstacles", "socp_traj_batch",
+           "socp_model_default_params", "socp_num_param", "socp_set_obstacles", "socp_traj_batch", "socp_traj_adaptive_batch",
            "socp_trace_width", "socp_trace_max_rows", "socp_trace_batch", "socp_point_batch", "socp_residual_batch", "socp_fdjac_batch", "socp_solve_batch",
            "socp_continuation_param_batch", "socp_continuation_boundary_batch",
            "socp_measure_fp64_peak"]
@@ -69,6 +70,7 @@ def lib():
     L.socp_num_param.argtypes = [sp]
     L.socp_set_obstacles.argtypes = [vp, ci, vp, vp, vp]
     L.socp_traj_batch.argtypes = [vp, ci, ci, cl, vp, vp, vp, vp, vp, vp, ci]
+    L.socp_traj_adaptive_batch.argtypes = [vp, ci, ci, cl, vp, vp, vp, vp, vp, cd, vp, vp, ci]
     L.socp_trace_width.argtypes = [ci]
     L.socp_trace_max_rows.argtypes = [ci, ci]
     L.socp_trace_batch.argtypes = [vp, ci, ci, cl, vp, vp, vp, vp, vp, vp, vp, vp, ci]

@@ -123,10 +123,13 @@ enum { SLOT_MPARAMS = 0, SLOT_SW, SLOT_T0, SLOT_TF, SLOT_X0, SLOT_XF, SLOT_AUX0,
 
 template <int MODEL>
 static void launch_traj(socp_ctx *ctx, long B, int S, const double *mp, const double *sw, const double *t0,
-                        const double *tf, const double *X0, double *Xf) {
+                        const double *tf, const double *X0, double *Xf, double tol = 0., int *nsteps = nullptr) {
     const int threads = 128;
     long blocks = (B + threads - 1) / threads;
-    traj_kernel<MODEL><<<(unsigned)blocks, threads, 0, ctx->stream>>>(B, S, mp, sw, t0, tf, X0, Xf, ctx->d_counters);
+    if (tol > 0.)
+        traj_kernel<MODEL, true><<<(unsigned)blocks, threads, 0, ctx->stream>>>(B, S, mp, sw, t0, tf, X0, Xf, ctx->d_counters, tol, nsteps);
+    else
+        traj_kernel<MODEL, false><<<(unsigned)blocks, threads, 0, ctx->stream>>>(B, S, mp, sw, t0, tf, X0, Xf, ctx->d_counters, 0., nullptr);
     ctx->launches += 1;
 }
 
@@ -249,6 +252,7 @@ int socp_get_stats(socp_ctx *ctx, socp_stats *out) {
     out->jac_ms = ctx->jac_ms;
     out->iterations = (double)c[1];
     out->jac_evals = (double)c[2];
+    out->dopri_steps = (double)c[3];
     if (getenv("SOCP_PHASE_CLOCKS")) {
         fprintf(stderr, "phase clocks (cycles): res");
         for (int k = 0; k < 8; ++k) fprintf(stderr, " %llu", c[16 + k]);
@@ -329,6 +333,39 @@ int socp_traj_batch(socp_ctx *ctx, int model_id, int step_nbr, long B, const dou
     }
     CUDA_TRY(ctx, cudaGetLastError());
     if ((rc = fetch_out(ctx, Xf, d_Xf, (size_t)B * N, mem)) != SOCP_OK) return rc;
+    if (mem == SOCP_HOST) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return SOCP_OK;
+}
+
+int socp_traj_adaptive_batch(socp_ctx *ctx, int model_id, int step_nbr, long B, const double *mparams,
+                             const double *sw, const double *t0, const double *tf, const double *X0,
+                             double tol, double *Xf, int *nsteps, int mem) {
+    if (!ctx) return SOCP_ERR_ARG;
+    if (model_id < 0 || model_id >= SOCP_NUM_MODELS || B < 0 || !mparams || !t0 || !tf || !X0 || !Xf || !(tol > 0.))
+        return fail(ctx, SOCP_ERR_ARG, "socp_traj_adaptive_batch: bad arguments");
+    if (B == 0) return SOCP_OK;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const int N = 2 * kDim[model_id], np = kNP[model_id];
+    const int S = step_nbr > 0 ? step_nbr : kSteps[model_id];
+    int rc = SOCP_OK;
+    const double *d_mp = stage_in(ctx, SLOT_MPARAMS, mparams, (size_t)B * np, mem, &rc);
+    const double *d_sw = stage_in(ctx, SLOT_SW, sw, (size_t)B * 2, mem, &rc);
+    const double *d_t0 = stage_in(ctx, SLOT_T0, t0, (size_t)B, mem, &rc);
+    const double *d_tf = stage_in(ctx, SLOT_TF, tf, (size_t)B, mem, &rc);
+    const double *d_X0 = stage_in(ctx, SLOT_X0, X0, (size_t)B * N, mem, &rc);
+    double *d_Xf = stage_out(ctx, SLOT_XF, Xf, (size_t)B * N, mem, &rc);
+    int *d_ns = stage_out(ctx, SLOT_INFO, nsteps, (size_t)B * 2, mem, &rc);
+    if (rc != SOCP_OK) return rc;
+    switch (model_id) {
+    case SOCP_GODDARD: launch_traj<GODDARD>(ctx, B, S, d_mp, d_sw, d_t0, d_tf, d_X0, d_Xf, tol, d_ns); break;
+    case SOCP_DOUBLE_INTEGRATOR: launch_traj<DOUBLE_INTEGRATOR>(ctx, B, S, d_mp, d_sw, d_t0, d_tf, d_X0, d_Xf, tol, d_ns); break;
+    case SOCP_COVID19: launch_traj<COVID19>(ctx, B, S, d_mp, d_sw, d_t0, d_tf, d_X0, d_Xf, tol, d_ns); break;
+    case SOCP_VTOL_UAV: launch_traj<VTOL_UAV>(ctx, B, S, d_mp, d_sw, d_t0, d_tf, d_X0, d_Xf, tol, d_ns); break;
+    case SOCP_INTERCEPTOR: launch_traj<INTERCEPTOR>(ctx, B, S, d_mp, d_sw, d_t0, d_tf, d_X0, d_Xf, tol, d_ns); break;
+    }
+    CUDA_TRY(ctx, cudaGetLastError());
+    if ((rc = fetch_out(ctx, Xf, d_Xf, (size_t)B * N, mem)) != SOCP_OK) return rc;
+    if ((rc = fetch_out(ctx, nsteps, d_ns, (size_t)B * 2, mem)) != SOCP_OK) return rc;
     if (mem == SOCP_HOST) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return SOCP_OK;
 }

@@ -48,6 +48,98 @@ SOCP_DEV int integrate_fixed(const typename Model<MODEL>::Ctx &c, double *X, dou
     return steps;
 }
 
+// ---- adaptive Dormand-Prince 5(4): the reference's -D_USE_BOOST build -----------------------------
+// odeTools.cpp:131-134: integrate_adaptive(make_dense_output<runge_kutta_dopri5>(tol, tol), model, X,
+// t0, tf, dt).  Restated from the published Boost.Odeint algorithm (runge_kutta_dopri5::do_step_impl,
+// default_error_checker, default_step_adjuster, integrate_adaptive for dense-output steppers); Boost is
+// not available to pin against, so parity is checked against the CPU restatement of the same algorithm only.
+// One thread owns the trajectory: state, the seven stage slopes and the step-size controller live in
+// registers; the error norm is a max over the thread's own components.
+template <int MODEL>
+SOCP_DEV void dopri5_try(const typename Model<MODEL>::Ctx &c, double t, const double *in, const double *k1, double dt,
+                         double *out, double *k7, double &err, double tol) {
+    typedef Model<MODEL> M;
+    constexpr int N = M::N;
+    const double a2 = 1.0 / 5, a3 = 3.0 / 10, a4 = 4.0 / 5, a5 = 8.0 / 9;
+    const double b21 = 1.0 / 5, b31 = 3.0 / 40, b32 = 9.0 / 40, b41 = 44.0 / 45, b42 = -56.0 / 15, b43 = 32.0 / 9,
+                 b51 = 19372.0 / 6561, b52 = -25360.0 / 2187, b53 = 64448.0 / 6561, b54 = -212.0 / 729,
+                 b61 = 9017.0 / 3168, b62 = -355.0 / 33, b63 = 46732.0 / 5247, b64 = 49.0 / 176, b65 = -5103.0 / 18656;
+    const double c1 = 35.0 / 384, c3 = 500.0 / 1113, c4 = 125.0 / 192, c5 = -2187.0 / 6784, c6 = 11.0 / 84;
+    const double dc1 = c1 - 5179.0 / 57600, dc3 = c3 - 7571.0 / 16695, dc4 = c4 - 393.0 / 640,
+                 dc5 = c5 - (-92097.0 / 339200), dc6 = c6 - 187.0 / 2100, dc7 = -1.0 / 40;
+    double k2[N], k3[N], k4[N], k5[N], k6[N], y[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) y[i] = in[i] + dt * b21 * k1[i];
+    M::rhs(c, t + dt * a2, y, k2);
+#pragma unroll
+    for (int i = 0; i < N; ++i) y[i] = in[i] + dt * b31 * k1[i] + dt * b32 * k2[i];
+    M::rhs(c, t + dt * a3, y, k3);
+#pragma unroll
+    for (int i = 0; i < N; ++i) y[i] = in[i] + dt * b41 * k1[i] + dt * b42 * k2[i] + dt * b43 * k3[i];
+    M::rhs(c, t + dt * a4, y, k4);
+#pragma unroll
+    for (int i = 0; i < N; ++i) y[i] = in[i] + dt * b51 * k1[i] + dt * b52 * k2[i] + dt * b53 * k3[i] + dt * b54 * k4[i];
+    M::rhs(c, t + dt * a5, y, k5);
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+        y[i] = in[i] + dt * b61 * k1[i] + dt * b62 * k2[i] + dt * b63 * k3[i] + dt * b64 * k4[i] + dt * b65 * k5[i];
+    M::rhs(c, t + dt, y, k6);
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+        out[i] = in[i] + dt * c1 * k1[i] + dt * c3 * k3[i] + dt * c4 * k4[i] + dt * c5 * k5[i] + dt * c6 * k6[i];
+    M::rhs(c, t + dt, out, k7);
+    err = 0.;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const double xe = dt * dc1 * k1[i] + dt * dc3 * k3[i] + dt * dc4 * k4[i] + dt * dc5 * k5[i] + dt * dc6 * k6[i] + dt * dc7 * k7[i];
+        const double e = fabs(xe) / (tol + tol * (fabs(in[i]) + fabs(dt) * fabs(k1[i])));
+        if (e > err || e != e) err = e;
+    }
+}
+
+// returns accepted steps; rejected attempts are added to `rejected`
+template <int MODEL>
+SOCP_DEV int integrate_adaptive(const typename Model<MODEL>::Ctx &c, double *X, double t0, double tf, double dt, double tol,
+                                int &rejected) {
+    constexpr int N = Model<MODEL>::N;
+    const double eps = 2.220446049250313e-16;
+    double t = t0, k1[N], out[N], k7[N];
+    bool have_deriv = false;
+    int steps = 0;
+    if (!(dt > 0.)) return 0;
+    while (tf - t > eps) {
+        while ((t + dt) - tf <= eps) {
+            if (!have_deriv) { Model<MODEL>::rhs(c, t, X, k1); have_deriv = true; }
+            int failed = 0;
+            bool ok = false;
+            while (!ok && failed < 500) {
+                double err;
+                dopri5_try<MODEL>(c, t, X, k1, dt, out, k7, err, tol);
+                if (err > 1.0 || err != err) {
+                    const double f = 0.9 * pow(err, -1.0 / 3.0);
+                    dt *= (f > 0.2 && f == f) ? f : 0.2;
+                    ++failed;
+                    ++rejected;
+                } else {
+                    t += dt;
+                    if (err < 0.5) {
+                        const double e5 = 1.0 / 3125.0;          // 5^-5
+                        dt *= 0.9 * pow(fmax(err, e5), -1.0 / 5.0);
+                    }
+                    ok = true;
+                }
+            }
+            if (!ok) return steps;
+#pragma unroll
+            for (int i = 0; i < N; ++i) { X[i] = out[i]; k1[i] = k7[i]; }
+            ++steps;
+        }
+        dt = tf - t;
+        have_deriv = false;
+    }
+    return steps;
+}
+
 // model::ComputeTraj for one segment.  For the interceptor `c.chart` / `c.stage` are updated and
 // left as the reference leaves its hidden state (the final state is converted back to chart 1
 // but currentChart is not reset, interceptor.cpp:214-216).
@@ -89,6 +181,17 @@ SOCP_DEV int compute_traj<INTERCEPTOR>(Model<INTERCEPTOR>::Ctx &c, double *X, do
     return steps;
 }
 
+// model::ComputeTraj with the adaptive integrator (the reference's Boost build).  The interceptor keeps
+// its own fixed-step loop there too (interceptor.cpp:104-130 calls RK4 directly).
+template <int MODEL>
+SOCP_DEV int compute_traj_adaptive(typename Model<MODEL>::Ctx &c, double *X, double t0, double tf, int S, double tol, int &rejected) {
+    return integrate_adaptive<MODEL>(c, X, t0, tf, (tf - t0) / S, tol, rejected);
+}
+template <>
+SOCP_DEV int compute_traj_adaptive<INTERCEPTOR>(Model<INTERCEPTOR>::Ctx &c, double *X, double t0, double tf, int S, double, int &) {
+    return compute_traj<INTERCEPTOR>(c, X, t0, tf, S);
+}
+
 template <int MODEL> SOCP_DEV void get_chart_stage(const typename Model<MODEL>::Ctx &, int &chart, int &stage) { chart = 1; stage = 0; }
 template <> SOCP_DEV void get_chart_stage<INTERCEPTOR>(const Model<INTERCEPTOR>::Ctx &c, int &chart, int &stage) { chart = c.chart; stage = c.stage; }
 template <int MODEL> SOCP_DEV void set_chart_stage(typename Model<MODEL>::Ctx &, int, int) {}
@@ -108,11 +211,12 @@ SOCP_DEV void count_steps(unsigned long long *counter, int steps) {
 }
 
 // ---- kernel: B independent trajectories ------------------------------------------------------
-template <int MODEL>
+template <int MODEL, bool ADAPTIVE>
 __global__ void __launch_bounds__(128)
 traj_kernel(long B, int S, const double *__restrict__ mparams, const double *__restrict__ sw,
             const double *__restrict__ t0, const double *__restrict__ tf,
-            const double *__restrict__ X0, double *__restrict__ Xf, unsigned long long *counter) {
+            const double *__restrict__ X0, double *__restrict__ Xf, unsigned long long *counter,
+            double ode_tol, int *__restrict__ nsteps) {
     typedef Model<MODEL> M;
     constexpr int N = M::N;
     long b = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -123,11 +227,14 @@ traj_kernel(long B, int S, const double *__restrict__ mparams, const double *__r
         double X[N];
 #pragma unroll
         for (int i = 0; i < N; ++i) X[i] = X0[b * N + i];
-        steps = compute_traj<MODEL>(c, X, t0[b], tf[b], S);
+        int rej = 0;
+        if (ADAPTIVE) steps = compute_traj_adaptive<MODEL>(c, X, t0[b], tf[b], S, ode_tol, rej);
+        else steps = compute_traj<MODEL>(c, X, t0[b], tf[b], S);
 #pragma unroll
         for (int i = 0; i < N; ++i) Xf[b * N + i] = X[i];
+        if (nsteps) { nsteps[2 * b] = steps; nsteps[2 * b + 1] = rej; }
     }
-    count_steps(counter, steps);
+    count_steps(counter + (ADAPTIVE ? 3 : 0), steps);
 }
 
 // ---- kernel: trajectories with the observer (model::Trace rows) ----------------------------------

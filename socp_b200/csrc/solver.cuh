@@ -48,6 +48,7 @@ struct SolverDev {
     // solver settings
     double xtol, epsfcn, factor;
     int maxfev, run_mode;
+    double ode_tol;                        // > 0: adaptive Dormand-Prince segments (socp_shape::ode_tol)
     // persistent state
     double *x, *xe, *fvec, *diag, *qtf, *wa1, *wa2, *wa3, *wa4, *scr, *fjac, *r, *ends, *jends, *dstate;
     int *istate;
@@ -186,7 +187,7 @@ SOCP_DEV double fd_step(double v, double epsfcn) {
 }
 
 // ---- kernel 1: integrate every requested shooting segment --------------------------------------
-template <int MODEL>
+template <int MODEL, bool ADAPTIVE>
 __global__ void __launch_bounds__(128)
 integrate_worklist(SolverDev D, int cur) {
     typedef Model<MODEL> M;
@@ -234,7 +235,8 @@ integrate_worklist(SolverDev D, int cur) {
 #pragma unroll
             for (int i = 0; i < N; ++i) if (i == kk) X[i] += h;
         }
-        steps += compute_traj<MODEL>(c, X, t1, t2, D.S);
+        if (ADAPTIVE) { int rej = 0; steps += compute_traj_adaptive<MODEL>(c, X, t1, t2, D.S, D.ode_tol, rej); }
+        else steps += compute_traj<MODEL>(c, X, t1, t2, D.S);
 #pragma unroll
         for (int i = 0; i < N; ++i) out[i] = X[i];
         int chart, stage;
@@ -242,7 +244,7 @@ integrate_worklist(SolverDev D, int cur) {
         out[N] = (double)chart;
         out[N + 1] = (double)stage;
     }
-    count_steps(D.counters, steps);
+    count_steps(D.counters + (ADAPTIVE ? 3 : 0), steps);
 }
 
 // ---- residual assembly (one thread) ------------------------------------------------------------

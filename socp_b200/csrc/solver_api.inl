@@ -39,6 +39,9 @@ int make_plan(socp_ctx *ctx, const socp_shape *shape, HostPlan &pl) {
     D.REC = D.N + 2;
     D.LR = P * (P + 1) / 2;
     D.nfree = P - D.N * D.M;
+    D.ode_tol = (shape->integrator == SOCP_DOPRI5) ? shape->ode_tol : 0.;
+    if (shape->integrator != SOCP_RK4 && shape->integrator != SOCP_DOPRI5) return fail(ctx, SOCP_ERR_ARG, "bad shape.integrator");
+    if (shape->integrator == SOCP_DOPRI5 && !(shape->ode_tol > 0.)) return fail(ctx, SOCP_ERR_ARG, "shape.ode_tol must be > 0 with SOCP_DOPRI5");
     for (int j = 0; j <= D.M; ++j) {
         const int mt = shape->mode_t[j];
         if (mt < SOCP_FIXED || mt > SOCP_CONTINUOUS) return fail(ctx, SOCP_ERR_ARG, "bad mode_t");
@@ -192,7 +195,8 @@ void launch_hybrd(socp_ctx *ctx, const SolverDev &D, int cur, int grid, int prof
 template <int MODEL>
 void launch_round(socp_ctx *ctx, const SolverDev &D, int cur, int grid_int, int grid_adv, int prof_slot) {
     if (prof_slot >= 0) cudaEventRecord(prof_event(ctx, kProfEv * prof_slot), ctx->stream);
-    integrate_worklist<MODEL><<<grid_int, 128, 0, ctx->stream>>>(D, cur);
+    if (D.ode_tol > 0.) integrate_worklist<MODEL, true><<<grid_int, 128, 0, ctx->stream>>>(D, cur);
+    else integrate_worklist<MODEL, false><<<grid_int, 128, 0, ctx->stream>>>(D, cur);
     if (prof_slot >= 0) cudaEventRecord(prof_event(ctx, kProfEv * prof_slot + 1), ctx->stream);
     assemble_kernel<MODEL><<<grid_int, 128, 0, ctx->stream>>>(D, cur);
     if (prof_slot >= 0) cudaEventRecord(prof_event(ctx, kProfEv * prof_slot + 2), ctx->stream);

@@ -44,9 +44,11 @@ def default_params(model_id):
     return out
 
 
-def make_shape(model_id, num_multi, mode_t, mode_X, step_nbr=0):
-    """shooting::SetMode(mode_t, mode_X) (shooting.cpp:185-199) as a plain struct."""
+def make_shape(model_id, num_multi, mode_t, mode_X, step_nbr=0, ode_tol=0.0):
+    """shooting::SetMode(mode_t, mode_X) (shooting.cpp:185-199) as a plain struct.  ode_tol > 0 selects
+    the adaptive Dormand-Prince integrator of the reference's Boost build (abs = rel = ode_tol)."""
     s = Shape()
+    s.integrator, s.ode_tol = (1, float(ode_tol)) if ode_tol and ode_tol > 0 else (0, 0.0)
     s.model_id, s.num_multi, s.step_nbr = int(model_id), int(num_multi), int(step_nbr or 0)
     dim = model_dim(model_id)
     if len(mode_t) != num_multi + 1 or len(mode_X) != num_multi + 1:
@@ -143,7 +145,7 @@ class Engine:
         return dict(rk4_steps=s.rk4_steps, kernel_launches=s.kernel_launches,
                     solver_rounds=s.solver_rounds, device_bytes=s.device_bytes,
                     integrate_ms=s.integrate_ms, integrate_launches=s.integrate_launches,
-                    advance_ms=s.advance_ms, advance_launches=s.advance_launches, assemble_ms=s.assemble_ms, jac_ms=s.jac_ms, iterations=s.iterations, jac_evals=s.jac_evals)
+                    advance_ms=s.advance_ms, advance_launches=s.advance_launches, assemble_ms=s.assemble_ms, jac_ms=s.jac_ms, iterations=s.iterations, jac_evals=s.jac_evals, dopri_steps=s.dopri_steps)
 
     def set_profiling(self, on=True):
         self._check(self._L.socp_set_profiling(self._h, int(bool(on))))
@@ -204,6 +206,20 @@ class Engine:
         self._check(self._L.socp_traj_batch(self._h, model_id, int(step_nbr or 0), B, a.inp(mparams), a.inp(sw),
                                             a.inp(t0), a.inp(tf), a.inp(X0), a.out(out), mem))
         return out
+
+    def traj_adaptive_batch(self, model_id, mparams, t0, X0, tf, tol, step_nbr=0, sw=None):
+        """ComputeTraj with the adaptive Dormand-Prince integrator (socp_traj_adaptive_batch); host arrays.
+        Returns (Xf[B][N], nsteps[B][2] = accepted steps, rejected attempts)."""
+        X0 = np.ascontiguousarray(X0, dtype=np.float64)
+        B, N = X0.shape
+        mparams = self._bcast_params(mparams, B, model_nparams(model_id))
+        t0 = np.broadcast_to(np.asarray(t0, dtype=np.float64), (B,))
+        tf = np.broadcast_to(np.asarray(tf, dtype=np.float64), (B,))
+        Xf, ns = np.empty((B, N)), np.zeros((B, 2), dtype=np.int32)
+        a = _Arg(HOST)
+        self._check(self._L.socp_traj_adaptive_batch(self._h, model_id, int(step_nbr or 0), B, a.inp(mparams), a.inp(sw),
+                                                     a.inp(t0), a.inp(tf), a.inp(X0), float(tol), a.out(Xf), a.out(ns), HOST))
+        return Xf, ns
 
     def trace_batch(self, model_id, mparams, t0, X0, tf, step_nbr=0, sw=None):
         """The observer form of ComputeTraj (socp_trace_batch): rows[B][R][W] = {t, X, control, H, extra}
