@@ -330,6 +330,33 @@ def main():
                                 "(socp_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 entry"},
                 "flops_per_rk4_step": flops, "kernels": kern}
 
+    # the RK4 trajectory kernel alone (BASELINE metric "RK4 steps/sec, % of FP64 roofline"): the Goddard
+    # batch of SURVEY 8d's microbenchmark, 2^20 trajectories of one 10-step segment, device resident
+    rk4_kernel = None
+    if rank == 0 or world > 1:
+        Bt = 1 << 20
+        reps = 6
+        Xi_t = torch.from_numpy(np.tile(x0[:1, :14], (Bt, 1)) * (1 + 1e-3 * np.random.default_rng(7).uniform(-1, 1, (Bt, 14)))).to(dev)
+        mp_t = d_mp[:1].repeat(Bt, 1).contiguous()
+        t0_t = torch.zeros(Bt, dtype=torch.float64, device=dev)
+        tf_t = torch.full((Bt,), 0.1 / 6, dtype=torch.float64, device=dev)
+        out_t = torch.empty_like(Xi_t)
+        for _ in range(3):
+            eng.traj_batch(sb.GODDARD, mp_t, t0_t, Xi_t, tf_t, 10, out=out_t)
+        eng.sync()
+        eng.reset_stats()
+        eng.timer_start()
+        for _ in range(reps):
+            eng.traj_batch(sb.GODDARD, mp_t, t0_t, Xi_t, tf_t, 10, out=out_t)
+        t_ms = eng.timer_stop()
+        steps_t = eng.stats()["rk4_steps"]
+        tf_ach = steps_t * flops / (t_ms * 1e-3) / 1e12
+        rk4_kernel = {"kernel": "traj_kernel<goddard>", "trajectories": Bt, "rk4_steps_per_s": steps_t / (t_ms * 1e-3),
+                      "ms_per_launch": t_ms / reps, "achieved": tf_ach, "peak": peak_tf, "unit": "TFLOP/s",
+                      "frac": tf_ach / peak_tf, "bound": "fp64", "flops_per_rk4_step": flops,
+                      "note": "inputs 117 MB + outputs 117 MB per launch (> L2 together with the solver workspace)"}
+        del Xi_t, mp_t, t0_t, tf_t, out_t
+
     # end to end through the public API with pinned host buffers
     e2e = None
     if rank == 0 or world > 1:
@@ -387,7 +414,7 @@ def main():
             "mean_nfev": float(agg[2].item()) / (world * B),
             "solver_rounds_per_step": st["solver_rounds"] / args.steps,
             "gpu_launches": int(st["kernel_launches"]),
-            "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu_baseline,
+            "roofline": roofline, "rk4_kernel": rk4_kernel, "e2e": e2e, "cpu_baseline": cpu_baseline,
             "clocks": sampler.summary(), "fp64_peak_probe_sm_mhz": clk,
         }
         print(json.dumps(line))

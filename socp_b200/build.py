@@ -29,6 +29,7 @@ def build(force=False, verbose=False, extra=()):
     if not force and not stale():
         return SO
     nvcc = os.environ.get("NVCC", "nvcc")
+    extra = list(extra) + os.environ.get("SOCP_NVCC_EXTRA", "").split()      # experiments: -DSOCP_...=...
     cmd = [nvcc] + NVCC_FLAGS + list(extra) + (["-Xptxas", "-v"] if verbose else []) + \
           ["-o", SO, os.path.join(CSRC, "api.cu")]
     r = subprocess.run(cmd, capture_output=True, text=True)

@@ -124,7 +124,7 @@ enum { SLOT_MPARAMS = 0, SLOT_SW, SLOT_T0, SLOT_TF, SLOT_X0, SLOT_XF, SLOT_AUX0,
 template <int MODEL>
 static void launch_traj(socp_ctx *ctx, long B, int S, const double *mp, const double *sw, const double *t0,
                         const double *tf, const double *X0, double *Xf, double tol = 0., int *nsteps = nullptr) {
-    const int threads = 128;
+    const int threads = SOCP_TRAJ_THREADS;
     long blocks = (B + threads - 1) / threads;
     if (tol > 0.)
         traj_kernel<MODEL, true><<<(unsigned)blocks, threads, 0, ctx->stream>>>(B, S, mp, sw, t0, tf, X0, Xf, ctx->d_counters, tol, nsteps);

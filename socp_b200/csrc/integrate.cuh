@@ -40,8 +40,7 @@ SOCP_DEV int integrate_fixed(const typename Model<MODEL>::Ctx &c, double *X, dou
     double t = t0;
     int steps = 0;
     while (t < (tf - dt / 2)) {
-        if (t + dt > tf) rk4_step<MODEL>(c, t, X, tf - t);
-        else rk4_step<MODEL>(c, t, X, dt);
+        rk4_step<MODEL>(c, t, X, (t + dt > tf) ? tf - t : dt);     // one inlined copy of the step
         t += dt;
         ++steps;
     }
@@ -211,8 +210,9 @@ SOCP_DEV void count_steps(unsigned long long *counter, int steps) {
 }
 
 // ---- kernel: B independent trajectories ------------------------------------------------------
+#define SOCP_TRAJ_THREADS 128      // threads per CTA of the trajectory kernels
 template <int MODEL, bool ADAPTIVE>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(SOCP_TRAJ_THREADS, Model<MODEL>::MINB)
 traj_kernel(long B, int S, const double *__restrict__ mparams, const double *__restrict__ sw,
             const double *__restrict__ t0, const double *__restrict__ tf,
             const double *__restrict__ X0, double *__restrict__ Xf, unsigned long long *counter,

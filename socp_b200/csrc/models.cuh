@@ -31,16 +31,20 @@ template <int MODEL> struct Model;
 // =============================== goddard ======================================================
 template <> struct Model<GODDARD> {
     static constexpr int DIM = 7, N = 14, NP = 8, NCTRL = 3, DEFAULT_STEPS = 10;
-    struct Ctx { double C, b, KD, kr, umax, mu1, mu2, sing, sw0, sw1; };
+    static constexpr int MINB = 1;      // CTAs/SM asked of the trajectory kernels: 240 registers, no spills (a cap of 168 costs 30%)
+    struct Ctx { double C, b, KD, kr, umax, mu1, mu2, sing, sw0, sw1, half_inv_mu2; };
     SOCP_DEV static void load(Ctx &c, const double *m, const double *sw) {
         c.C = m[0]; c.b = m[1]; c.KD = m[2]; c.kr = m[3]; c.umax = m[4]; c.mu1 = m[5]; c.mu2 = m[6];
         c.sing = m[7];
+        c.half_inv_mu2 = 0.5 / c.mu2;     // hoisted out of the RHS: alpha_u = -Switch / 2 / mu2
         c.sw0 = sw ? sw[0] : 0.0227;      // goddard.cpp:27-29
         c.sw1 = sw ? sw[1] : 0.08;
     }
 
-    // goddard.cpp:188-253 (true singular control), expression order of the reference
-    SOCP_DEV static double singular(const Ctx &c, const double *X) {
+    // goddard.cpp:188-253 (true singular control), expression order of the reference.  Out of line:
+    // it is only reached with mu2 == 0 inside the switching window, and inlining its ~600 instructions
+    // into every RHS copy of the RK4 loop overflows the instruction cache.
+    __device__ __noinline__ static double singular(const Ctx &c, const double *X) {
         double x = X[0], y = X[1], z = X[2], vx = X[3], vy = X[4], vz = X[5], mass = X[6];
         double p_x = X[7], p_y = X[8], p_z = X[9], p_vx = X[10], p_vy = X[11], p_vz = X[12];
         double r = sqrt(x * x + y * y + z * z);
@@ -76,20 +80,23 @@ template <> struct Model<GODDARD> {
     }
 
     // goddard.cpp:104-185.  Returns the control and |u| (= min(|alpha_u|, u_max)).
+    // |p_v| and 1/|p_v| come from one rsqrt (a sqrt plus a divide otherwise).
     SOCP_DEV static void control_norm(const Ctx &c, double t, const double *X, double minv,
                                       double *u, double &norm_u) {
         double p_vx = X[10], p_vy = X[11], p_vz = X[12], p_mass = X[13];
-        double norm_pv = sqrt(p_vx * p_vx + p_vy * p_vy + p_vz * p_vz);
+        double pv2 = p_vx * p_vx + p_vy * p_vy + p_vz * p_vz;
+        double pvinv = rsqrt(pv2);
+        double norm_pv = pv2 * pvinv;
         double Switch = c.mu1 - c.b * p_mass - c.C * minv * norm_pv;
         double alpha_u = 0.0;
         if (c.mu2 > 0) {
-            if (Switch < 0) alpha_u = -Switch / 2 / c.mu2;
+            if (Switch < 0) alpha_u = -Switch * c.half_inv_mu2;
         } else {
             if (t <= c.sw0) alpha_u = 1.0;
             else if (t <= c.sw1) alpha_u = (c.sing < 0) ? singular(c, X) : c.sing;
         }
         double a = fabs(alpha_u);
-        double scale = -alpha_u / norm_pv;          // u = -p_v * alpha_u / |p_v|
+        double scale = -alpha_u * pvinv;            // u = -p_v * alpha_u / |p_v|
         norm_u = a;
         if (a > c.umax) { scale = scale / a * c.umax; norm_u = c.umax; }
         u[0] = p_vx * scale; u[1] = p_vy * scale; u[2] = p_vz * scale;
@@ -103,11 +110,13 @@ template <> struct Model<GODDARD> {
     SOCP_DEV static void rhs(const Ctx &c, double t, const double *X, double *dX) {
         double x = X[0], y = X[1], z = X[2], vx = X[3], vy = X[4], vz = X[5], mass = X[6];
         double p_x = X[7], p_y = X[8], p_z = X[9], p_vx = X[10], p_vy = X[11], p_vz = X[12];
+        // r, 1/r and v, 1/v from one rsqrt each (instead of a sqrt and a divide)
         double r2 = x * x + y * y + z * z;
-        double r = sqrt(r2);
-        double rinv = 1.0 / r;
-        double v = sqrt(vx * vx + vy * vy + vz * vz);
-        double vinv = 1.0 / v;
+        double rinv = rsqrt(r2);
+        double r = r2 * rinv;
+        double v2 = vx * vx + vy * vy + vz * vz;
+        double vinv = rsqrt(v2);
+        double v = v2 * vinv;
         double minv = 1.0 / mass;
         double pvdotv = p_vx * vx + p_vy * vy + p_vz * vz;
         double ex = exp(-c.kr * (r - 1));
@@ -159,6 +168,7 @@ template <> struct Model<GODDARD> {
 // =============================== doubleIntegrator =============================================
 template <> struct Model<DOUBLE_INTEGRATOR> {
     static constexpr int DIM = 6, N = 12, NP = 3, NCTRL = 3, DEFAULT_STEPS = 30;
+    static constexpr int MINB = 1;
     struct Ctx { double umax, amax, muT; };
     SOCP_DEV static void load(Ctx &c, const double *m, const double *) { c.umax = m[0]; c.amax = m[1]; c.muT = m[2]; }
     // doubleIntegrator.cpp:218-259
@@ -191,6 +201,7 @@ template <> struct Model<DOUBLE_INTEGRATOR> {
 // =============================== covid19 ======================================================
 template <> struct Model<COVID19> {
     static constexpr int DIM = 4, N = 8, NP = 8, NCTRL = 1, DEFAULT_STEPS = 1000;
+    static constexpr int MINB = 1;
     struct Ctx { double R0, Tinf, Tinc, Npop, Imax, muI, umin, umax; };
     SOCP_DEV static void load(Ctx &c, const double *m, const double *) {
         c.R0 = m[0]; c.Tinf = m[1]; c.Tinc = m[2]; c.Npop = m[3]; c.Imax = m[4]; c.muI = m[5];
@@ -283,6 +294,7 @@ SOCP_DEV void obstacle_eval(double muObs, double phiObs, const double *pos, doub
 
 template <> struct Model<VTOL_UAV> {
     static constexpr int DIM = 6, N = 12, NP = 13, NCTRL = 3, DEFAULT_STEPS = 100;
+    static constexpr int MINB = 4;      // 128 registers: +45% throughput (occupancy hides the tanh chains)
     struct Ctx { double umax, amax, alphaT, alphaV, invSigma, Vd, ca, phiObs, muObs; };
     SOCP_DEV static void load(Ctx &c, const double *m, const double *) {
         c.umax = m[0]; c.amax = m[1]; c.alphaT = m[2]; c.alphaV = m[3]; c.invSigma = m[4];
@@ -336,6 +348,7 @@ template <> struct Model<VTOL_UAV> {
 
 template <> struct Model<INTERCEPTOR> {
     static constexpr int DIM = 6, N = 12, NP = 17, NCTRL = 2, DEFAULT_STEPS = 50;
+    static constexpr int MINB = 4;      // 128 registers: +65% throughput (occupancy hides the sin/cos chains)
     struct Ctx {
         double c0, hr, d0, eta, mprop, mempty, q, ve, alphamax, umax, mugft, muT, muV, muC;
         int chart, stage;

@@ -188,7 +188,7 @@ SOCP_DEV double fd_step(double v, double epsfcn) {
 
 // ---- kernel 1: integrate every requested shooting segment --------------------------------------
 template <int MODEL, bool ADAPTIVE>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, Model<MODEL>::MINB)
 integrate_worklist(SolverDev D, int cur) {
     typedef Model<MODEL> M;
     constexpr int N = M::N;
