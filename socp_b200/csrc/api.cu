@@ -258,6 +258,8 @@ int socp_get_stats(socp_ctx *ctx, socp_stats *out) {
         for (int k = 0; k < 8; ++k) fprintf(stderr, " %llu", c[16 + k]);
         fprintf(stderr, " | jac");
         for (int k = 0; k < 8; ++k) fprintf(stderr, " %llu", c[32 + k]);
+        fprintf(stderr, " | sub");
+        for (int k = 0; k < 8; ++k) fprintf(stderr, " %llu", c[48 + k]);
         fprintf(stderr, " | iterations %llu jac_evals %llu\n", c[1], c[2]);
     }
     return SOCP_OK;

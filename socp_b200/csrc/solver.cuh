@@ -56,6 +56,7 @@ struct SolverDev {
     int *lists;
     int *counts;
     unsigned long long *counters;      // [0] RK4 steps, [1] Broyden iterations, [2] Jacobian factorisations, [16+k] / [32+k] phase clocks
+    int sm_count;                      // multiprocessors of the device (seq_warp)
     int phase_clocks;                  // debugging aid (SOCP_PHASE_CLOCKS=1): accumulate clock64() per phase
 };
 
@@ -70,6 +71,25 @@ struct SolverDev {
             phase_t0 = now_;                                                                  \
         }                                                                                     \
     } while (0)
+
+// finer marks inside a phase (same clock, slots 48..63); sub_t0 is the caller's running time stamp
+#define SOCP_SUB(k)                                                                           \
+    do {                                                                                      \
+        if (clk_on && (threadIdx.x % G) == 0) {                                               \
+            const long long now_ = clock64();                                                 \
+            atomicAdd(clk_counters + 48 + (k), (unsigned long long)(now_ - sub_t0));          \
+            sub_t0 = now_;                                                                    \
+        }                                                                                     \
+    } while (0)
+
+// Which warp of a thread group runs the strictly sequential phases (Givens sweeps, back substitution).
+// Warp w of every CTA is scheduled on sub-partition w % 4 of its SM, so if every resident CTA used warp 0
+// all the sequential chains of an SM would share ONE scheduler and FP64 pipe while three idle (measured:
+// 1.7x slower per problem with 4 co-resident CTAs).  Co-resident CTAs are b, b + #SMs, b + 2 #SMs, ...:
+// rotate by blockIdx.x / #SMs.
+template <int G> SOCP_DEV int seq_warp(int sm_count) {
+    return (G == 32) ? 0 : (int)((blockIdx.x / (unsigned)sm_count) % (G / 32));
+}
 
 // ---- group helpers ---------------------------------------------------------------------------
 template <int G> SOCP_DEV void gsync() { if (G == 32) __syncwarp(); else __syncthreads(); }
@@ -398,8 +418,23 @@ assemble_kernel(SolverDev D, int cur) {
 // chosen so that a group touches consecutive addresses (coalesced in HBM, conflict-free in shared
 // memory when ldq is odd).  Every routine starts and ends with a group barrier.
 
+// copy with eight independent loads in flight per thread (a plain loop serialises on the memory latency)
 template <int G> SOCP_DEV void gcopy(double *dst, const double *src, int n) {
-    for (int i = threadIdx.x % G; i < n; i += G) dst[i] = src[i];
+    const int tid = threadIdx.x % G;
+    for (int base = 0; base < n; base += 8 * G) {
+        double t[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { const int i = base + k * G + tid; t[k] = (i < n) ? src[i] : 0.; }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { const int i = base + k * G + tid; if (i < n) dst[i] = t[k]; }
+    }
+}
+
+// ask L2 for [p, p + bytes): one prefetch per 128-byte line, spread over the group
+template <int G> SOCP_DEV void l2_prefetch(const void *p, size_t bytes) {
+    const char *c = (const char *)p;
+    for (size_t off = (size_t)(threadIdx.x % G) * 128; off < bytes; off += (size_t)G * 128)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(c + off));
 }
 
 SOCP_DEV double warp_sum(double v) {
@@ -425,22 +460,38 @@ SOCP_DEV double dot4(const double *a, const double *b, int m) {
 
 // qrfac (no pivoting) fused with "qtf = Q^T fvec" (the Householder reflections are applied to
 // qtf as one more column); rdiag/acnorm as in MINPACK.  One thread per column.
+// Both routines skip work on EXACT zeros: hi[k] is the last row of column k that is not an exact zero
+// (the shooting Jacobian is block bidiagonal plus a border, and Householder reflections keep the
+// lower band), so reflector j only spans rows j..hi[j] and a column whose dot product with it is an
+// exact zero is left alone.  The skipped operations would add or subtract exact zeros: the factors are
+// the ones the dense MINPACK loops produce (up to the sign of a zero).
 template <int G>
-__device__ void qrfac_g(int n, double *a, int lda, double *rdiag, double *acnorm, double *qtf, double *red) {
-    const int tid = threadIdx.x % G;
+__device__ void qrfac_g(int n, double *a, int lda, double *rdiag, double *acnorm, double *qtf, double *red, int rot, int *hi) {
+    // `rot` rotates the warp that owns the first columns: the active columns always start at thread 0, so
+    // without it the co-resident CTAs of an SM would all load the same scheduler (see seq_warp)
+    const int tid = (threadIdx.x + 32 * rot) % G;
     gsync<G>();
     for (int j = tid >> 5; j < n; j += G / 32) {       // column norms, one warp per column
         const double v = enorm_warp(n, a + (size_t)j * lda);
         if ((tid & 31) == 0) acnorm[j] = v;
     }
+    for (int k = tid; k <= n; k += G) {                // last non-zero row of every column (qtf: dense)
+        int last = (k < n) ? 0 : n - 1;
+        if (k < n) {
+            const double *ck = a + (size_t)k * lda;
+            for (int i = n - 1; i > 0; --i) if (ck[i] != 0.) { last = i; break; }
+        }
+        hi[k] = last;
+    }
     gsync<G>();
     for (int j = 0; j < n; ++j) {
         double *cj = a + (size_t)j * lda;
-        double ajnorm = enorm_g<G>(n - j, cj + j, red);
+        const int hj = max(hi[j], j), len = hj - j + 1;
+        double ajnorm = enorm_g<G>(len, cj + j, red);
         if (ajnorm != 0.) {
             if (cj[j] < 0.) ajnorm = -ajnorm;
             gsync<G>();
-            for (int i = j + tid; i < n; i += G) {
+            for (int i = j + tid; i <= hj; i += G) {
                 double v = cj[i] / ajnorm;
                 if (i == j) v += 1.;
                 cj[i] = v;
@@ -449,9 +500,12 @@ __device__ void qrfac_g(int n, double *a, int lda, double *rdiag, double *acnorm
             const double ajj = cj[j];
             for (int k = j + 1 + tid; k <= n; k += G) {  // remaining columns, and qtf as column n
                 double *ck = (k < n) ? a + (size_t)k * lda : qtf;
-                const double sum = dot4(cj + j, ck + j, n - j);
-                const double temp = sum / ajj;
-                for (int i = j; i < n; ++i) ck[i] -= temp * cj[i];
+                const double sum = dot4(cj + j, ck + j, len);
+                if (sum != 0.) {
+                    const double temp = sum / ajj;
+                    for (int i = j; i <= hj; ++i) ck[i] -= temp * cj[i];
+                    if (hi[k] < hj) hi[k] = hj;
+                }
             }
         }
         if (tid == 0) rdiag[j] = -ajnorm;
@@ -473,23 +527,26 @@ __device__ void pack_r_g(int n, const double *a, int lda, const double *rdiag, d
 
 // qform: accumulate Q (n x n) in place from the Householder vectors; wa is scratch [n]
 template <int G>
-__device__ void qform_g(int n, double *q, int lda, double *wa) {
-    const int tid = threadIdx.x % G;
+__device__ void qform_g(int n, double *q, int lda, double *wa, int rot, const int *hi) {
+    const int tid = (threadIdx.x + 32 * rot) % G;
     for (int j = 1 + tid; j < n; j += G)
         for (int i = 0; i < j; ++i) q[i + (size_t)j * lda] = 0.;
     gsync<G>();
     for (int l = 0; l < n; ++l) {
         const int k = n - 1 - l;
         double *ck = q + (size_t)k * lda;
-        for (int i = k + tid; i < n; i += G) { wa[i] = ck[i]; ck[i] = (i == k) ? 1. : 0.; }
+        const int hk = max(hi[k], k), len = hk - k + 1;    // reflector k spans rows k..hk (zeros below)
+        for (int i = k + tid; i <= hk; i += G) { wa[i] = ck[i]; ck[i] = (i == k) ? 1. : 0.; }
         gsync<G>();
         const double wk = wa[k];
         if (wk != 0.) {
             for (int j = k + tid; j < n; j += G) {
                 double *cj = q + (size_t)j * lda;
-                const double sum = dot4(cj + k, wa + k, n - k);
-                const double temp = sum / wk;
-                for (int i = k; i < n; ++i) cj[i] -= temp * wa[i];
+                const double sum = dot4(cj + k, wa + k, len);
+                if (sum != 0.) {
+                    const double temp = sum / wk;
+                    for (int i = k; i <= hk; ++i) cj[i] -= temp * wa[i];
+                }
             }
         }
         gsync<G>();
@@ -514,7 +571,9 @@ __device__ void rmulv_g(int n, const double *r, const double *v, const double *a
 // dogleg: x <- step; wa1, wa2 scratch
 template <int G>
 __device__ void dogleg_g(int n, const double *r, const double *diag, const double *qtb, double delta,
-                         double *x, double *wa1, double *wa2, double *red) {
+                         double *x, double *wa1, double *wa2, double *red, int seqw, bool clk_on = false,
+                         unsigned long long *clk_counters = nullptr) {
+    long long sub_t0 = clock64();
     const int tid = threadIdx.x % G;
     const int lane = threadIdx.x & 31;
     gsync<G>();
@@ -532,22 +591,27 @@ __device__ void dogleg_g(int n, const double *r, const double *diag, const doubl
             if (temp == 0.) temp = EPSMCH;
         }
         wa2[j] = temp;
+        wa1[j] = 1. / temp;
         x[j] = qtb[j];
     }
     gsync<G>();
-    if (tid < 32) {
+    if ((tid >> 5) == seqw) {
         double bj = x[n - 1];                                  // rhs of the pivot row (owner lane)
         for (int j = n - 1; j >= 0; --j) {
             const int owner = j & 31, next_owner = (j - 1) & 31;
             double cr = 0., cx = 0.;                           // next pivot row: fetched before x[j] is known
             if (j > 0 && lane == next_owner) { cr = r[rowstart(n, j - 1) + 1]; cx = x[j - 1]; }
-            const double xj = __shfl_sync(0xffffffffu, bj / wa2[j], owner);
+            // x[j] = bj / d without a divide on the chain: reciprocal (prepared above), residual, correction
+            const double d = wa2[j], dinv = wa1[j];
+            const double q0 = bj * dinv;
+            const double xj = __shfl_sync(0xffffffffu, fma(fma(-q0, d, bj), dinv, q0), owner);
             if (lane == owner) x[j] = xj;
             if (j > 0 && lane == next_owner) { bj = cx - cr * xj; x[j - 1] = bj; }
             for (int i = lane; i < j - 1; i += 32) x[i] -= r[rowstart(n, i) + (j - i)] * xj;
         }
     }
     gsync<G>();
+    SOCP_SUB(5);
     for (int j = tid; j < n; j += G) { wa1[j] = 0.; wa2[j] = diag[j] * x[j]; }
     gsync<G>();
     const double qnorm = enorm_g<G>(n, wa2, red);
@@ -580,6 +644,7 @@ __device__ void dogleg_g(int n, const double *r, const double *diag, const doubl
     gsync<G>();
     for (int j = tid; j < n; j += G) x[j] = temp * wa1[j] + alpha * x[j];
     gsync<G>();
+    SOCP_SUB(6);
 }
 
 // Givens rotation that maps (a, b) to (rho, 0) with MINPACK's conventions (r1updt): the coefficient
@@ -610,7 +675,9 @@ SOCP_DEV double givens_tau(double a, double b, double c, double sgl) {
 // r1updt on the packed upper-triangular factor (m == n): (R + u v^T) -> R' with the 2(n-1) Givens
 // rotations recorded in v and w for r1mpyq.  cs/sn are scratch [n] each, tmp is scratch [2n].
 template <int G>
-__device__ void r1updt_g(int n, double *s, const double *u, double *v, double *w, double *cs, double *sn, double *tmp) {
+__device__ void r1updt_g(int n, double *s, const double *u, double *v, double *w, double *cs, double *sn, double *tmp,
+                         int seqw, bool clk_on = false, unsigned long long *clk_counters = nullptr) {
+    long long sub_t0 = clock64();
     const int tid = threadIdx.x % G;
     const int lane = threadIdx.x & 31;
     const unsigned FULL = 0xffffffffu;
@@ -619,7 +686,7 @@ __device__ void r1updt_g(int n, double *s, const double *u, double *v, double *w
     // before step j is +-sqrt(sum_{k > j} v[k]^2) carrying the sign of the entry that last dominated
     // (|vn| < |v[k]|), or of v[n-1].  Both are suffix scans, so warp 0 forms all rotations at once
     // instead of walking the scalar recurrence.
-    if (tid < 32) {
+    if ((tid >> 5) == seqw) {
         double *SS = tmp;                              // SS[k] = sum_{q >= k} v[q]^2
         int *IDX = (int *)(tmp + n);                   // smallest dominating index above k within the lane's chunk
         double *TAU = w;                               // w is written only after this phase
@@ -685,6 +752,7 @@ __device__ void r1updt_g(int n, double *s, const double *u, double *v, double *w
         }
     }
     gsync<G>();
+    SOCP_SUB(2);
     // apply to the columns: column i is touched by rotations j = min(i, n-2) .. 0
     for (int i = tid; i < n; i += G) {
         double wi = (i == n - 1) ? s[rowstart(n, n - 1)] : 0.;
@@ -699,10 +767,11 @@ __device__ void r1updt_g(int n, double *s, const double *u, double *v, double *w
         w[i] = wi + v[n - 1] * u[i];                 // add the spike from the rank-1 update
     }
     gsync<G>();
+    SOCP_SUB(3);
     // Second sweep: eliminate the spike; rotation j depends on w[j] after rotations 0..j-1, strictly
     // sequential in j.  Warp 0: each lane owns the columns i = lane (mod 32) for the whole sweep (no
     // barrier inside the loop); the pivot w[j+1] is carried in a register and broadcast by one shuffle.
-    if (tid < 32) {
+    if ((tid >> 5) == seqw) {
         double wj = w[0];
         double sjj = s[0];
         for (int j = 0; j < n - 1; ++j) {
@@ -715,7 +784,10 @@ __device__ void r1updt_g(int n, double *s, const double *u, double *v, double *w
             if (wj != 0.) {                                        // uniform: wj is the same in every lane
                 double c, sgl;
                 givens(sjj, wj, c, sgl);
-                if (lane == (j & 31)) { s[jj] = c * sjj + sgl * wj; w[j] = givens_tau(sjj, wj, c, sgl); }
+                if (lane == (j & 31)) {
+                    s[jj] = c * sjj + sgl * wj;
+                    cs[j] = c; sn[j] = sgl; tmp[j] = (fabs(sjj) < fabs(wj)) ? 1. : 0.;     // tau is formed after the sweep
+                }
                 if (lane == nown) { s[jj + 1] = c * c1 + sgl * c2; carry = -sgl * c1 + c * c2; w[j + 1] = carry; }
                 for (int i = j + 2 + ((lane - j - 2) & 31); i < n; i += 32) {
                     const int l = jj + (i - j);
@@ -724,12 +796,19 @@ __device__ void r1updt_g(int n, double *s, const double *u, double *v, double *w
                     w[i] = -sgl * sl + c * wi;
                 }
             }
+            else if (lane == (j & 31)) tmp[j] = 2.;                 // no rotation: w[j] stays zero
             wj = __shfl_sync(FULL, carry, nown);
             sjj = sjj_next;
+        }
+        // MINPACK's tau for r1mpyq (one divide each, off the sequential chain); entries written by this lane
+        for (int j = lane; j < n - 1; j += 32) {
+            if (tmp[j] == 1.) w[j] = (fabs(cs[j]) * DBL_MAX > 1.) ? 1. / cs[j] : 1.;
+            else if (tmp[j] == 0.) w[j] = sn[j];
         }
         if (lane == ((n - 1) & 31)) s[rowstart(n, n - 1)] = w[n - 1];
     }
     gsync<G>();
+    SOCP_SUB(4);
 }
 
 // Rotation coefficients as r1mpyq reconstructs them from the stored tau values: scr = [c1 s1 c2 s2][n]
@@ -804,7 +883,7 @@ __device__ void dogleg_and_request(const SolverDev &D, long b, const Work &W, in
                                    int *next_res, int *next_cnt) {
     const int n = D.P, tid = threadIdx.x % G;
     const double delta = ds[D_DELTA];
-    dogleg_g<G>(n, W.r, W.diag, W.qtf, delta, W.wa1, W.wa2, W.wa3, red);
+    dogleg_g<G>(n, W.r, W.diag, W.qtf, delta, W.wa1, W.wa2, W.wa3, red, seq_warp<G>(D.sm_count), D.phase_clocks, D.counters);
     for (int j = tid; j < n; j += G) {
         const double pj = -W.wa1[j];
         W.wa1[j] = pj;
@@ -879,6 +958,7 @@ hybrd_res_kernel(SolverDev D, int cur, int per_group_doubles) {
         W.r = STAGE_R ? vec + 13 * n : D.r + (size_t)b * D.LR;
         W.q = D.fjac + (size_t)b * n * n;
         W.ldq = n;
+        l2_prefetch<G>(W.q, (size_t)n * n * sizeof(double));      // Q is first touched ~20 us from now
         gcopy<G>(W.x, D.x + b * n, n); gcopy<G>(W.xe, D.xe + b * n, n); gcopy<G>(W.fvec, D.fvec + b * n, n);
         gcopy<G>(W.diag, D.diag + b * n, n); gcopy<G>(W.qtf, D.qtf + b * n, n); gcopy<G>(W.wa1, D.wa1 + b * n, n);
         gcopy<G>(W.wa4, D.wa4 + b * n, n);
@@ -960,33 +1040,47 @@ hybrd_res_kernel(SolverDev D, int cur, int per_group_doubles) {
             SOCP_PHASE(16, 2);
             {
                 const int lane = threadIdx.x & 31, warp = tid >> 5;
-                constexpr int NW = G / 32;
-                for (int j0 = warp * 4; j0 < n; j0 += NW * 4) {
-                    double part[4] = {0., 0., 0., 0.};
-                    for (int i = lane; i < n; i += 32) {
-                        const double wi = W.wa4[i];
+                constexpr int NW = G / 32, NC = 8;
+                const bool clk_on = D.phase_clocks; unsigned long long *clk_counters = D.counters; long long sub_t0 = clock64();
+                for (int j0 = warp * NC; j0 < n; j0 += NW * NC) {
+                    double part[NC];
 #pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            if (j0 + k < n) part[k] += W.q[(size_t)(j0 + k) * W.ldq + i] * wi;
-                    }
+                    for (int k = 0; k < NC; ++k) part[k] = 0.;
+                    for (int i0 = 0; i0 < n; i0 += 96) {          // 3 x 8 loads in flight per lane
+                        double q[3][NC];
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const int j = j0 + k;
-                        if (j < n) {
-                            const double sum = warp_sum(part[k]);
-                            if (lane == 0) {
-                                W.wa2[j] = (sum - W.wa3[j]) / pnorm;
-                                W.wa1[j] = W.diag[j] * ((W.diag[j] * W.wa1[j]) / pnorm);
-                                if (ratio >= p0001) W.qtf[j] = sum;
-                            }
+                        for (int u = 0; u < 3; ++u) {
+                            const int i = i0 + 32 * u + lane;
+#pragma unroll
+                            for (int k = 0; k < NC; ++k)
+                                q[u][k] = (i < n && j0 + k < n) ? W.q[(size_t)(j0 + k) * W.ldq + i] : 0.;
+                        }
+#pragma unroll
+                        for (int u = 0; u < 3; ++u) {
+                            const int i = i0 + 32 * u + lane;
+                            const double wi = (i < n) ? W.wa4[i] : 0.;
+#pragma unroll
+                            for (int k = 0; k < NC; ++k) part[k] = fma(q[u][k], wi, part[k]);
                         }
                     }
+                    SOCP_SUB(0);
+#pragma unroll
+                    for (int k = 0; k < NC; ++k) {
+                        const int j = j0 + k;
+                        const double sum = warp_sum(part[k]);
+                        if (j < n && lane == 0) {
+                            W.wa2[j] = (sum - W.wa3[j]) / pnorm;
+                            W.wa1[j] = W.diag[j] * ((W.diag[j] * W.wa1[j]) / pnorm);
+                            if (ratio >= p0001) W.qtf[j] = sum;
+                        }
+                    }
+                    SOCP_SUB(1);
                 }
             }
             if (tid == 0) atomicAdd(D.counters + 1, 1ULL);
             gsync<G>();
             SOCP_PHASE(16, 3);
-            r1updt_g<G>(n, W.r, W.wa1, W.wa2, W.wa3, W.scr, W.scr + n, W.scr + 2 * n);
+            r1updt_g<G>(n, W.r, W.wa1, W.wa2, W.wa3, W.scr, W.scr + n, W.scr + 2 * n, seq_warp<G>(D.sm_count), D.phase_clocks, D.counters);
             SOCP_PHASE(16, 4);
             r1coef_g<G>(n, W.wa2, W.wa3, W.scr);
             r1mpyq_g<G>(n, n, W.q, W.ldq, W.scr);
@@ -1051,7 +1145,8 @@ hybrd_jac_kernel(SolverDev D, int cur, int per_group_doubles) {
         if (tid == 0) { is[I_NFEV] += n; is[I_JEVAL] = 1; atomicAdd(D.counters + 2, 1ULL); }
         for (int i = tid; i < n; i += G) W.qtf[i] = W.fvec[i];
         // wa1 = rdiag, wa2 = acnorm
-        qrfac_g<G>(n, W.q, W.ldq, W.wa1, W.wa2, W.qtf, red);
+        int *hi = (int *)W.scr;                            // [n + 1] last non-zero row per column (scr is free here)
+        qrfac_g<G>(n, W.q, W.ldq, W.wa1, W.wa2, W.qtf, red, seq_warp<G>(D.sm_count), hi);
         SOCP_PHASE(32, 1);
         if (is[I_ITER] == 1) {
             for (int j = tid; j < n; j += G) {
@@ -1069,7 +1164,7 @@ hybrd_jac_kernel(SolverDev D, int cur, int per_group_doubles) {
         }
         pack_r_g<G>(n, W.q, W.ldq, W.wa1, W.r);
         SOCP_PHASE(32, 2);
-        qform_g<G>(n, W.q, W.ldq, W.wa1);
+        qform_g<G>(n, W.q, W.ldq, W.wa1, seq_warp<G>(D.sm_count), hi);
         SOCP_PHASE(32, 3);
         for (int j = tid; j < n; j += G) W.diag[j] = fmax(W.diag[j], W.wa2[j]);
         gsync<G>();

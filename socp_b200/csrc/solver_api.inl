@@ -259,6 +259,7 @@ int run_solver(socp_ctx *ctx, const socp_shape *shape, long B, const double *d_m
     }
     D.xtol = xtol; D.epsfcn = epsfcn; D.factor = 1.0; D.maxfev = maxfev; D.run_mode = run_mode;
     D.counters = ctx->d_counters;
+    D.sm_count = ctx->sm_count;
     D.phase_clocks = getenv("SOCP_PHASE_CLOCKS") ? 1 : 0;
     const int grid_int = ctx->sm_count * 8;
     const int grid_adv = ctx->sm_count * 6;
