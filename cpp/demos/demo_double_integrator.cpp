@@ -4,6 +4,7 @@
 // (muT -> 0.02).  Prints one machine-readable line per stage:
 //   stage <k> info <i> nfev <n> tf <%.17g> p0 <six costates %.17g>
 #include <cstdio>
+#include <cstdlib>
 #include <iostream>
 #include <vector>
 
@@ -12,13 +13,14 @@
 
 static void report(int stage, int info, shooting & s, int dim, int numParam) {
 	std::vector<int> calls = s.GetCallNumber();
-	printf("stage %d info %d nfev %d tf %.17g p0", stage, info, calls[0], s.GetParameters(numParam - 1));
+	printf("stage %d info %d nfev %d njev %d tf %.17g p0", stage, info, calls[0], calls[1], s.GetParameters(numParam - 1));
 	for (int i = 0; i < dim; i++) printf(" %.17g", s.GetParameters(dim + i));
 	printf("\n");
 }
 
-int main() {
-	doubleIntegrator my_model(0, "");				// modelOrder 0: forward-difference Jacobian (hybrd)
+int main(int argc, char **argv) {
+	const int order = argc > 1 ? atoi(argv[1]) : 0;	// 0: forward-difference Jacobian (hybrd); 1: analytic (hybrj)
+	doubleIntegrator my_model(order, "");
 	const int dim = my_model.GetDim();
 	shooting my_shooting(my_model, 1, 1);
 	my_shooting.SetPrecision(1e-8);

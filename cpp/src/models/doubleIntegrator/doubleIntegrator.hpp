@@ -1,7 +1,7 @@
 // cpp/src/models/doubleIntegrator/doubleIntegrator.hpp -- mirror of
-// src/models/doubleIntegrator/doubleIntegrator.hpp:16-79.  modelOrder is accepted as in the
-// reference; this engine always solves with the forward-difference Powell hybrid (hybrd), the
-// analytic-Jacobian path (hybrj, modelOrder == 1) is not built yet.
+// src/models/doubleIntegrator/doubleIntegrator.hpp:16-79.  modelOrder 0: forward-difference Powell
+// hybrid (hybrd); modelOrder 1: analytic Jacobian from the variational integration (hybrj), both on
+// the device.
 #include "../../socp/model.hpp"
 
 #include <iostream>

@@ -66,10 +66,12 @@ model::mstate model::ModelInt(real const& t0, mstate const& X, real const& tf, i
 	const int N = 2 * dim;
 	mstate Xs(X);
 	if (isJac) {
-		// the variational integration (state + sensitivities, doubleIntegrator.cpp:113-213) has no device
-		// kernel yet; the engine differentiates by forward differences instead
-		std::cerr << std::endl << "ERROR : isJac = 1 (variational integration) is not available in the B200 engine" << std::endl;
-		exit(1);
+		// variational integration (state + sensitivities): device kernel for the models that have the
+		// equations -- the double integrator, as in the reference (doubleIntegrator.cpp:113-213)
+		if ((int)X.size() != (N + 1) * N) { std::cerr << std::endl << "ERROR : isJac = 1 needs a (2n+1)*2n state" << std::endl; exit(1); }
+		if (socp_traj_var_batch(dc.ctx, dc.id, DeviceSteps(), 1, dc.mp.data(), &t0, &tf, X.data(), Xs.data(), SOCP_HOST) != SOCP_OK)
+			die("socp_traj_var_batch", dc.ctx);
+		return Xs;
 	}
 	std::vector<real> Xin(X.begin(), X.begin() + N), Xout(N);
 	if (isTrace) {

@@ -318,11 +318,16 @@ int shooting::SolveShootingFunction(int const & numParam, std::vector<real> & pa
 	std::vector<real> mp = myModel.DeviceParams(), Xb;
 	for (int j = 0; j <= data->numMulti; j++)
 		Xb.insert(Xb.end(), data->X[j].begin(), data->X[j].begin() + data->dim);
-	// modelOrder == 1 (analytic Jacobian, hybrj, shooting.cpp:830-851) is solved with the
-	// forward-difference Powell hybrid as well: njev stays 0 and nfev counts the FD columns
-	data->njev = 0;
-	int rc = socp_solve_batch(ctx, &shape, 1, mp.data(), data->time.data(), Xb.data(), param.data(), data->xtol, data->maxfev,
-	                          &data->info, &data->nfev, &data->fnorm, SOCP_HOST);
+	int rc;
+	if (myModel.modelOrder == 0) {
+		data->njev = 0;
+		rc = socp_solve_batch(ctx, &shape, 1, mp.data(), data->time.data(), Xb.data(), param.data(), data->xtol, data->maxfev,
+		                      &data->info, &data->nfev, &data->fnorm, SOCP_HOST);
+	} else {
+		// analytic Jacobian from the variational integration (hybrj, shooting.cpp:830-851)
+		rc = socp_solve_hybrj_batch(ctx, &shape, 1, mp.data(), data->time.data(), Xb.data(), param.data(), data->xtol, data->maxfev,
+		                            &data->info, &data->nfev, &data->njev, &data->fnorm, SOCP_HOST);
+	}
 	if (rc != SOCP_OK && rc != SOCP_ERR_ARG) {
 		std::cerr << std::endl << "socp_b200: " << socp_last_error(ctx) << std::endl;
 		exit(1);

@@ -163,6 +163,21 @@ int socp_solve_batch(socp_ctx *ctx, const socp_shape *shape, long B, const doubl
                      const double *time, const double *Xb, double *x, double xtol, int maxfev,
                      int *info, int *nfev, double *fnorm, int mem);
 
+/* The analytic-Jacobian path, modelOrder == 1 (shooting.cpp:830-851: hybrj on
+ * StaticShootingFunctionJacobian, :877-915).  Only the double integrator has variational equations
+ * (doubleIntegrator.cpp:113-213), as in the reference; other models return SOCP_ERR_UNSUPPORTED.
+ *   socp_traj_var_batch     model::ComputeTraj(isJac = 1): X0/Xf are [B][(2dim+1) 2dim] extended states
+ *                           (state, then the sensitivity rows X[2dim (k+1) + i] = dX_k/dX0_i, shooting.cpp:1003)
+ *   socp_jacobian_batch     shooting::ShootingFunctionJacobian (shooting.cpp:996-1130), column-major like fjac
+ *   socp_solve_hybrj_batch  the Powell hybrid with that Jacobian; nfev counts residuals, njev Jacobians */
+int socp_traj_var_batch(socp_ctx *ctx, int model_id, int step_nbr, long B, const double *mparams,
+                        const double *t0, const double *tf, const double *X0, double *Xf, int mem);
+int socp_jacobian_batch(socp_ctx *ctx, const socp_shape *shape, long B, const double *mparams,
+                        const double *time, const double *Xb, const double *x, double *fjac, int mem);
+int socp_solve_hybrj_batch(socp_ctx *ctx, const socp_shape *shape, long B, const double *mparams,
+                           const double *time, const double *Xb, double *x, double xtol, int maxfev,
+                           int *info, int *nfev, int *njev, double *fnorm, int mem);
+
 /* shooting::SolveShootingContinuation on a model parameter (shooting.cpp:695-778), every problem
  * running its own homotopy b in (0,1] with step halving.  mparams is updated in place (entry
  * param_idx ends at goal[b] on success).  goal is [B].  calls is [B][2] = {solver calls, total

@@ -65,6 +65,11 @@ def lib():
         L.so_fdjac.argtypes = [pp, _dp, cd, _dp]
         L.so_solve.argtypes = [pp, _dp, cd, ci, ctypes.POINTER(ci), _dp]
         L.so_solve.restype = ci
+        L.so_traj_var.argtypes = [pp, cd, _dp, cd, _dp]
+        L.so_jacobian.argtypes = [pp, _dp, _dp]
+        L.so_jacobian.restype = ci
+        L.so_solve_hybrj.argtypes = [pp, _dp, cd, ci, ctypes.POINTER(ci), ctypes.POINTER(ci), _dp]
+        L.so_solve_hybrj.restype = ci
         L.so_continuation_param.argtypes = [pp, _dp, cd, ci, cd, ci, cd, cd, ctypes.POINTER(ci)]
         L.so_continuation_param.restype = ci
         L.so_continuation_boundary.argtypes = [pp, _dp, cd, ci, cd, _dp, ctypes.c_void_p, _dp,
@@ -219,6 +224,28 @@ class OracleProblem:
         fnorm = np.zeros(1)
         info = lib().so_solve(ctypes.byref(self.p), _d(x), xtol, maxfev, ctypes.byref(nfev), _d(fnorm))
         return dict(x=x, info=info, nfev=nfev.value, fnorm=fnorm[0])
+
+    # -- analytic-Jacobian path (modelOrder == 1: the double integrator) ------------------------
+    def traj_var(self, t0, X0, tf):
+        """model::ComputeTraj(isJac = 1): X0 is the (2n+1) 2n extended state."""
+        X0 = _arr(X0)
+        out = np.zeros(X0.size)
+        lib().so_traj_var(ctypes.byref(self.p), float(t0), _d(X0), float(tf), _d(out))
+        return out
+
+    def jacobian(self, x):
+        x = _arr(x)
+        out = np.zeros(x.size * x.size)
+        rc = lib().so_jacobian(ctypes.byref(self.p), _d(x), _d(out))
+        assert rc == 0, "model has no variational equations"
+        return out.reshape(x.size, x.size).T.copy()     # J[i, j]
+
+    def solve_hybrj(self, x, xtol=1e-8, maxfev=10000):
+        x = _arr(x).copy()
+        nfev, njev = ctypes.c_int(0), ctypes.c_int(0)
+        fnorm = np.zeros(1)
+        info = lib().so_solve_hybrj(ctypes.byref(self.p), _d(x), xtol, maxfev, ctypes.byref(nfev), ctypes.byref(njev), _d(fnorm))
+        return dict(x=x, info=info, nfev=nfev.value, njev=njev.value, fnorm=fnorm[0])
 
     def continuation_param(self, x, step, param_idx, goal, xtol=1e-8, maxfev=10000, step_min=1e-12):
         x = _arr(x).copy()

@@ -1153,6 +1153,227 @@ static int residual_cb(void *ud, int n, const double *x, double *fvec, int iflag
     return 0;
 }
 
+/* ================= analytic Jacobian path (modelOrder == 1, hybrj) ======================== */
+/* Only the double integrator implements it in the reference (doubleIntegrator.cpp:113-213, :264-300).
+ * Extended state: X[0..N) then the sensitivity rows X[N(k+1) + i] = dX_k / dX0_i (shooting.cpp:1003). */
+#define SO_NV (SO_MAX_N * (SO_MAX_N + 1))
+
+int so_has_variational(const so_problem *p) { return p->model_id == SO_DI; }
+
+/* doubleIntegrator::ModelJacobian: [f ; (df/dX) Phi] with the reference's CONSTANT df/dX (the velocity
+ * rows carry -1 on the p_v columns whatever a_max and the saturation, "a revoir en cas de saturation",
+ * doubleIntegrator.cpp:167-169) and its dense triple loop (zero terms included, same summation order) */
+static void di_rhs_var(so_problem *p, const double *X, double *dX)
+{
+    const int N = 12;
+    static const int col[12] = {3, 4, 5, 9, 10, 11, -1, -1, -1, 6, 7, 8};
+    static const double val[12] = {1, 1, 1, -1, -1, -1, 0, 0, 0, -1, -1, -1};
+    di_rhs(p, X, dX);
+    for (int i = 0; i < N; ++i)
+        for (int j = 0; j < N; ++j) {
+            double acc = 0;
+            for (int k = 0; k < N; ++k) acc += ((k == col[i]) ? val[i] : 0.0) * X[N * (k + 1) + j];
+            dX[N + N * i + j] = acc;
+        }
+}
+
+/* doubleIntegrator::Hamiltonian(isJac = 1): (dH/dX, dH/dt) */
+static void di_H_grad(const double *X, double *g)
+{
+    g[0] = 0; g[1] = 0; g[2] = 0; g[3] = X[6]; g[4] = X[7]; g[5] = X[8];
+    g[6] = X[3]; g[7] = X[4]; g[8] = X[5]; g[9] = -X[9]; g[10] = -X[10]; g[11] = -X[11]; g[12] = 0;
+}
+
+/* model::ComputeTraj(isJac = 1): the same fixed-step RK4 (odeTools.cpp:89-98, :128-146) on the
+ * (2n+1) 2n vector */
+void so_traj_var(so_problem *p, double t0, const double *X0, double tf, double *Xf)
+{
+    const int N = 2 * p->dim, NV = N * (N + 1);
+    double X[SO_NV], F1[SO_NV], F2[SO_NV], F3[SO_NV], F4[SO_NV], Y[SO_NV];
+    memcpy(X, X0, sizeof(double) * NV);
+    const double dt = (tf - t0) / p->step_nbr;
+    double t = t0;
+    while (t < (tf - dt / 2)) {
+        const double h = (t + dt > tf) ? tf - t : dt;
+        di_rhs_var(p, X, F1);
+        for (int i = 0; i < NV; ++i) Y[i] = X[i] + (h / 2.0) * F1[i];
+        di_rhs_var(p, Y, F2);
+        for (int i = 0; i < NV; ++i) Y[i] = X[i] + (h / 2.0) * F2[i];
+        di_rhs_var(p, Y, F3);
+        for (int i = 0; i < NV; ++i) Y[i] = X[i] + h * F3[i];
+        di_rhs_var(p, Y, F4);
+        for (int i = 0; i < NV; ++i) X[i] = X[i] + (h / 6.0) * (F1[i] + (F4[i] + 2.0 * (F2[i] + F3[i])));
+        t += dt;
+        ++p->rk4_steps;
+    }
+    memcpy(Xf, X, sizeof(double) * NV);
+}
+
+static void seed_identity(const double *state, int N, double *X)
+{
+    memset(X, 0, sizeof(double) * N * (N + 1));
+    for (int i = 0; i < N; ++i) { X[i] = state[i]; X[N * (i + 1) + i] = 1; }
+}
+
+/* rows of d(boundary function)/d(node unknowns [, time]) as model::Initial/FinalFunction and the H
+ * variants build them (model.hpp:104-120, :149-183, :214-226, :256-290); `width` = N or N + 1 */
+static void boundary_jac(so_problem *p, double t, const double *X, const int *mode_X, int with_H, double *func)
+{
+    const int n = p->dim, N = 2 * n, width = with_H ? N + 1 : N;
+    double f[SO_MAX_N], g[SO_MAX_N + 1];
+    if (with_H) so_rhs(p, t, X, f);
+    for (int j = 0; j < n; ++j) {
+        const int row = (mode_X[j] == SO_FREE) ? j + n : j;
+        for (int i = 0; i < N; ++i) func[width * j + i] = X[N * (row + 1) + i];
+        if (with_H) func[width * j + N] = f[row];
+    }
+    if (with_H) {
+        di_H_grad(X, g);
+        for (int i = 0; i < N; ++i) {
+            double acc = 0;
+            for (int k = 0; k < N; ++k) acc += g[k] * X[N * (k + 1) + i];
+            func[width * n + i] = acc;
+        }
+        double acc = 0;
+        for (int k = 0; k < N; ++k) acc += g[k] * f[k];
+        func[width * n + N] = acc + g[N];
+    }
+}
+
+/* shooting::ShootingFunctionJacobian (shooting.cpp:996-1130) + the transpose of
+ * StaticShootingFunctionJacobian (:889-893): fjac column-major, fjac[i + P j] = dF_i / dx_j */
+int so_jacobian(so_problem *p, const double *x, double *fjac)
+{
+    if (!so_has_variational(p)) return -1;
+    const int n = p->dim, N = 2 * n, M = p->num_multi, P = so_num_param(p), W4 = 4 * n + 1;
+    double tl[SO_MAX_NODES];
+    so_timeline(p, x, tl);
+    double *J = (double *)calloc((size_t)P * P, sizeof(double));      /* row-major, as the reference fills it */
+    double X_t0[SO_NV], X1[SO_NV], X_tf[SO_NV], Xp[SO_NV], func[(SO_MAX_DIM + 1) * (SO_MAX_N + 1)];
+    double funcMS[SO_MAX_N * (4 * SO_MAX_DIM + 1)], sf[4 * SO_MAX_DIM + 1];
+    seed_identity(x, N, X_t0);
+    memcpy(X1, X_t0, sizeof X1);
+    int nbr = N * M;
+    for (int i = 0; i < M; ++i) {
+        const double t1 = tl[i], t2 = tl[i + 1];
+        so_traj_var(p, t1, X1, t2, X_tf);
+        const int index = N * (i + 1);
+        if (i == 0) {
+            if (p->mode_t[0] == SO_FIXED) {
+                boundary_jac(p, tl[0], X1, p->mode_X[0], 0, func);
+                for (int k = 0; k < n; ++k)
+                    for (int j = 0; j < N; ++j) J[P * k + j] = func[N * k + j];
+            } else {
+                boundary_jac(p, tl[0], X1, p->mode_X[0], 1, func);
+                for (int k = 0; k < n; ++k) {
+                    for (int j = 0; j < N; ++j) J[P * k + j] = func[(N + 1) * k + j];
+                    J[P * k + nbr] = func[(N + 1) * k + N];
+                }
+                for (int j = 0; j < N; ++j) J[P * nbr + j] = func[(N + 1) * n + j];
+                J[P * nbr + nbr] = func[(N + 1) * n + N];
+                nbr += 1;
+            }
+        }
+        if (i < M - 1) {
+            seed_identity(x + index, N, Xp);
+            /* shooting::MultipleShootingFunction(isJac = 1), shooting.cpp:1511-1576 */
+            double fxt[SO_MAX_N], fxp[SO_MAX_N];
+            so_rhs(p, t2, X_tf, fxt);
+            so_rhs(p, t2, Xp, fxp);
+            memset(funcMS, 0, sizeof funcMS);
+            const int free_t = p->mode_t[i + 1] == SO_FREE;
+            for (int j = 0; j < n; ++j) {
+                const int m = p->mode_X[i + 1][j];
+                if (m == SO_FIXED) {
+                    for (int q = 0; q < N; ++q) {
+                        funcMS[W4 * j + q] = X_tf[N * (j + 1) + q];
+                        funcMS[W4 * (j + n) + N + q] = Xp[N * (j + 1) + q];
+                    }
+                    if (free_t) { funcMS[W4 * j + 4 * n] = fxt[j]; funcMS[W4 * (j + n) + 4 * n] = fxp[j]; }
+                } else if (m == SO_CONTINUOUS) {
+                    for (int q = 0; q < N; ++q) {
+                        funcMS[W4 * j + q] = X_tf[N * (j + 1) + q];
+                        funcMS[W4 * j + N + q] = -Xp[N * (j + 1) + q];
+                        funcMS[W4 * (j + n) + q] = X_tf[N * (j + n + 1) + q];
+                        funcMS[W4 * (j + n) + N + q] = -Xp[N * (j + n + 1) + q];
+                    }
+                    if (free_t) {
+                        funcMS[W4 * j + 4 * n] = fxt[j] - fxp[j];
+                        funcMS[W4 * (j + n) + 4 * n] = fxt[j + n] - fxp[j + n];
+                    }
+                }   /* FREE interior state: model::SwitchingStateFunction is empty by default (model.hpp:339) */
+            }
+            const int ncols = free_t ? W4 : 4 * n;
+            for (int k = 0; k < N; ++k) {
+                for (int j = 0; j < ncols; ++j) J[P * (index + k) + (index - N + j)] = funcMS[W4 * k + j];
+                if (free_t) J[P * (index + k) + nbr] = funcMS[W4 * k + 4 * n];
+            }
+            if (free_t) {
+                /* model::SwitchingTimesFunction(isJac = 1), model.hpp:306-327 */
+                double gX[SO_MAX_N + 1], gP[SO_MAX_N + 1];
+                di_H_grad(X_tf, gX);
+                di_H_grad(Xp, gP);
+                memset(sf, 0, sizeof sf);
+                for (int q = 0; q < N; ++q)
+                    for (int k = 0; k < N; ++k) {
+                        sf[q] += gX[k] * X_tf[N * (k + 1) + q];
+                        sf[N + q] -= gP[k] * Xp[N * (k + 1) + q];
+                    }
+                for (int k = 0; k < N; ++k) sf[4 * n] += gX[k] * fxt[k] - gP[k] * fxp[k];
+                sf[4 * n] += gX[N] - gP[N];
+                for (int j = 0; j < 4 * n; ++j) J[P * nbr + (index - N + j)] = sf[j];
+                J[P * nbr + nbr] = sf[4 * n];
+                nbr += 1;
+            }
+            memcpy(X1, Xp, sizeof X1);
+        }
+        if (i == M - 1) {
+            if (p->mode_t[M] == SO_FIXED) {
+                boundary_jac(p, t2, X_tf, p->mode_X[M], 0, func);
+                for (int k = 0; k < n; ++k)
+                    for (int j = 0; j < N; ++j) J[P * (n + k) + (N * i + j)] = func[N * k + j];
+            } else {
+                boundary_jac(p, t2, X_tf, p->mode_X[M], 1, func);
+                for (int k = 0; k < n; ++k) {
+                    for (int j = 0; j < N; ++j) J[P * (n + k) + (N * i + j)] = func[(N + 1) * k + j];
+                    J[P * (n + k) + nbr] = func[(N + 1) * k + N];
+                }
+                for (int j = 0; j < N; ++j) J[P * nbr + (N * i + j)] = func[(N + 1) * n + j];
+                J[P * nbr + nbr] = func[(N + 1) * n + N];
+                nbr += 1;
+            }
+        }
+    }
+    for (int k = 0; k < P; ++k)
+        for (int j = 0; j < P; ++j) fjac[k + P * j] = J[P * k + j];
+    free(J);
+    return 0;
+}
+
+static int residual_jac_cb(void *ud, int n, const double *x, double *fvec, double *fjac, int ldfjac, int iflag)
+{
+    (void)n; (void)ldfjac;
+    if (iflag == 1) so_residual((so_problem *)ud, x, fvec);
+    else so_jacobian((so_problem *)ud, x, fjac);
+    return 0;
+}
+
+/* shooting::SolveShootingFunction, modelOrder == 1 branch (shooting.cpp:830-851) */
+int so_solve_hybrj(so_problem *p, double *x, double xtol, int maxfev, int *nfev, int *njev, double *fnorm)
+{
+    int P = so_num_param(p);
+    int lr = P * (P + 1) / 2;
+    double *w = (double *)calloc((size_t)(P * P + lr + 7 * P), sizeof(double));
+    double *fjac = w, *r = fjac + P * P, *qtf = r + lr, *fvec = qtf + P, *diag = fvec + P;
+    double *wa1 = diag + P, *wa2 = wa1 + P, *wa3 = wa2 + P, *wa4 = wa3 + P;
+    for (int i = 0; i < P; ++i) diag[i] = 1;
+    int info = hybrj(residual_jac_cb, p, P, x, fvec, fjac, P, xtol, maxfev, diag, 1, 1.0, 0, nfev, njev,
+                     r, lr, qtf, wa1, wa2, wa3, wa4);
+    if (fnorm) *fnorm = mp_enorm(P, fvec);
+    free(w);
+    return info;
+}
+
 /* forward-difference Jacobian with MINPACK's step rule (fdjac1, dense), column-major */
 void so_fdjac(so_problem *p, const double *x0, double epsfcn, double *fjac)
 {

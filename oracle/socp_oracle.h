@@ -82,6 +82,11 @@ void so_integrate_adaptive(so_problem *p, double *X, double t0, double tf, doubl
 void so_timeline(so_problem *p, const double *x, double *tl);                     /* shooting.cpp:1579 */
 void so_residual(so_problem *p, const double *x, double *fvec);                   /* shooting.cpp:918 */
 void so_fdjac(so_problem *p, const double *x, double epsfcn, double *fjac);       /* column-major */
+/* analytic-Jacobian path (modelOrder == 1; the double integrator only, as in the reference) */
+int so_has_variational(const so_problem *p);
+void so_traj_var(so_problem *p, double t0, const double *X0, double tf, double *Xf);   /* (2n+1) 2n doubles */
+int so_jacobian(so_problem *p, const double *x, double *fjac);                         /* shooting.cpp:996-1130, column-major */
+int so_solve_hybrj(so_problem *p, double *x, double xtol, int maxfev, int *nfev, int *njev, double *fnorm);
 
 /* SolveShootingFunction (shooting.cpp:781): hybrd with SOCP's settings. Returns info. */
 int so_solve(so_problem *p, double *x, double xtol, int maxfev, int *nfev, double *fnorm);

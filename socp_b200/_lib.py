@@ -36,6 +36,7 @@ SYMBOLS = ["socp_create", "socp_destroy", "socp_last_error", "socp_set_stream", 
            "socp_model_dim", "socp_model_nparams", "socp_model_default_steps",
            "socp_model_default_params", "socp_num_param", "socp_set_obstacles", "socp_traj_batch", "socp_traj_adaptive_batch",
            "socp_trace_width", "socp_trace_max_rows", "socp_trace_batch", "socp_point_batch", "socp_residual_batch", "socp_fdjac_batch", "socp_solve_batch",
+           "socp_traj_var_batch", "socp_jacobian_batch", "socp_solve_hybrj_batch",
            "socp_continuation_param_batch", "socp_continuation_boundary_batch",
            "socp_measure_fp64_peak"]
 
@@ -78,6 +79,9 @@ def lib():
     L.socp_residual_batch.argtypes = [vp, sp, cl, vp, vp, vp, vp, vp, ci]
     L.socp_fdjac_batch.argtypes = [vp, sp, cl, vp, vp, vp, vp, cd, vp, ci]
     L.socp_solve_batch.argtypes = [vp, sp, cl, vp, vp, vp, vp, cd, ci, vp, vp, vp, ci]
+    L.socp_traj_var_batch.argtypes = [vp, ci, ci, cl, vp, vp, vp, vp, vp, ci]
+    L.socp_jacobian_batch.argtypes = [vp, sp, cl, vp, vp, vp, vp, vp, ci]
+    L.socp_solve_hybrj_batch.argtypes = [vp, sp, cl, vp, vp, vp, vp, cd, ci, vp, vp, vp, vp, ci]
     L.socp_continuation_param_batch.argtypes = [vp, sp, cl, vp, vp, vp, vp, cd, ci, cd, ci, vp, cd, vp, vp]
     L.socp_continuation_boundary_batch.argtypes = [vp, sp, cl, vp, vp, vp, vp, vp, vp, cd, ci, cd, cd, vp, vp]
     L.socp_measure_fp64_peak.argtypes = [vp, P(cd), P(cd)]

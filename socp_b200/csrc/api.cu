@@ -10,6 +10,7 @@
 #include <vector>
 #include <algorithm>
 #include <map>
+#include <type_traits>
 
 #include "../../include/socp_b200.h"
 #include "models.cuh"

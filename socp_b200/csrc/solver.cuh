@@ -31,7 +31,7 @@ namespace socp {
 enum { PH_IDLE = 0, PH_F0 = 1, PH_JAC = 2, PH_TRIAL = 3 };
 enum { RUN_SOLVE = 0, RUN_RESIDUAL = 1, RUN_FDJAC = 2 };
 // per-problem integer state
-enum { I_PHASE = 0, I_ITER, I_NCSUC, I_NCFAIL, I_NSLOW1, I_NSLOW2, I_JEVAL, I_NFEV, I_INFO, I_BASE, I_COUNT = 12 };
+enum { I_PHASE = 0, I_ITER, I_NCSUC, I_NCFAIL, I_NSLOW1, I_NSLOW2, I_JEVAL, I_NFEV, I_INFO, I_BASE, I_NJEV, I_COUNT = 12 };
 // per-problem scalar state
 enum { D_DELTA = 0, D_XNORM, D_FNORM, D_PNORM, D_COUNT = 4 };
 
@@ -49,6 +49,7 @@ struct SolverDev {
     double xtol, epsfcn, factor;
     int maxfev, run_mode;
     double ode_tol;                        // > 0: adaptive Dormand-Prince segments (socp_shape::ode_tol)
+    int analytic;                          // 1: hybrj -- Jacobian requests are served by the variational integration
     // persistent state
     double *x, *xe, *fvec, *diag, *qtf, *wa1, *wa2, *wa3, *wa4, *scr, *fjac, *r, *ends, *jends, *dstate;
     int *istate;
@@ -212,7 +213,7 @@ __global__ void __launch_bounds__(128, Model<MODEL>::MINB)
 integrate_worklist(SolverDev D, int cur) {
     typedef Model<MODEL> M;
     constexpr int N = M::N;
-    const int nres = D.counts[cur * 2 + 0], njac = D.counts[cur * 2 + 1];
+    const int nres = D.counts[cur * 2 + 0], njac = D.analytic ? 0 : D.counts[cur * 2 + 1];
     const int *res_list = D.lists + (size_t)(cur * 2 + 0) * D.B;
     const int *jac_list = D.lists + (size_t)(cur * 2 + 1) * D.B;
     if (blockIdx.x == 0 && threadIdx.x == 0) {       // next-next round's counters
@@ -384,7 +385,7 @@ __device__ __noinline__ void assemble(const SolverDev &D, long b, int col, doubl
 template <int MODEL>
 __global__ void __launch_bounds__(128)
 assemble_kernel(SolverDev D, int cur) {
-    const int nres = D.counts[cur * 2 + 0], njac = D.counts[cur * 2 + 1];
+    const int nres = D.counts[cur * 2 + 0], njac = D.analytic ? 0 : D.counts[cur * 2 + 1];
     const int *res_list = D.lists + (size_t)(cur * 2 + 0) * D.B;
     const int *jac_list = D.lists + (size_t)(cur * 2 + 1) * D.B;
     const int n = D.P;
@@ -408,6 +409,243 @@ assemble_kernel(SolverDev D, int cur) {
             const double *fvec = D.fvec + b * n;
             assemble<MODEL>(D, b, j, h, be, D.jends + (size_t)b * D.nJ * D.REC, colj);
             for (int i = 0; i < n; ++i) colj[i] = (colj[i] - fvec[i]) / h;      // fdjac1
+        }
+    }
+}
+
+// ---- analytic-Jacobian path (modelOrder == 1, hybrj): variational segments ----------------------
+// Restates model::ComputeTraj(isJac = 1) for the double integrator (doubleIntegrator.cpp:113-213): the
+// extended state is X[0..N) plus the sensitivity rows X[N(k+1) + i] = dX_k / dX0_i, seeded with the
+// identity (shooting.cpp:1003-1005).  Every sensitivity COLUMN obeys the same linear system, so a group
+// of 16 lanes owns one segment: lane i < N integrates (X, Phi[:, i]) -- the state redundantly, identical
+// in every lane -- with the same RK4 and combination order as the plain trajectory.
+template <int MODEL> struct Variational { static constexpr bool HAS = false; };
+template <> struct Variational<DOUBLE_INTEGRATOR> {
+    static constexpr bool HAS = true;
+    // (df/dX) phi with the reference's constant matrix (doubleIntegrator.cpp:161-172: -1 on the p_v
+    // columns of the velocity rows whatever a_max and the saturation)
+    SOCP_DEV static void rhs(const double *phi, double *d) {
+        d[0] = phi[3]; d[1] = phi[4]; d[2] = phi[5];
+        d[3] = -phi[9]; d[4] = -phi[10]; d[5] = -phi[11];
+        d[6] = 0.; d[7] = 0.; d[8] = 0.;
+        d[9] = -phi[6]; d[10] = -phi[7]; d[11] = -phi[8];
+    }
+    // doubleIntegrator::Hamiltonian(isJac = 1): (dH/dX, dH/dt)  (doubleIntegrator.cpp:293-296)
+    SOCP_DEV static void hgrad(const double *X, double *g) {
+        g[0] = 0.; g[1] = 0.; g[2] = 0.; g[3] = X[6]; g[4] = X[7]; g[5] = X[8];
+        g[6] = X[3]; g[7] = X[4]; g[8] = X[5]; g[9] = -X[9]; g[10] = -X[10]; g[11] = -X[11]; g[12] = 0.;
+    }
+};
+
+// one lane: (X, phi) over [t0, tf] with S RK4 steps; returns steps
+template <int MODEL>
+SOCP_DEV int var_traj_lane(const typename Model<MODEL>::Ctx &c, double *X, double *phi, double t0, double tf, int S) {
+    typedef Model<MODEL> M;
+    typedef Variational<MODEL> V;
+    constexpr int N = M::N;
+    const double dt = (tf - t0) / S;
+    double t = t0;
+    int steps = 0;
+    while (t < (tf - dt / 2)) {
+        const double h = (t + dt > tf) ? tf - t : dt, h2 = h / 2.0, h6 = h / 6.0;
+        double F1[N], F23[N], F[N], Y[N], G1[N], G23[N], G[N], Z[N];
+        M::rhs(c, t, X, F1); V::rhs(phi, G1);
+#pragma unroll
+        for (int i = 0; i < N; ++i) { Y[i] = X[i] + h2 * F1[i]; Z[i] = phi[i] + h2 * G1[i]; }
+        M::rhs(c, t + h2, Y, F23); V::rhs(Z, G23);
+#pragma unroll
+        for (int i = 0; i < N; ++i) { Y[i] = X[i] + h2 * F23[i]; Z[i] = phi[i] + h2 * G23[i]; }
+        M::rhs(c, t + h2, Y, F); V::rhs(Z, G);
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            F23[i] = F23[i] + F[i]; Y[i] = X[i] + h * F[i];
+            G23[i] = G23[i] + G[i]; Z[i] = phi[i] + h * G[i];
+        }
+        M::rhs(c, t + h, Y, F); V::rhs(Z, G);
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            X[i] = X[i] + h6 * (F1[i] + (F[i] + 2.0 * F23[i]));
+            phi[i] = phi[i] + h6 * (G1[i] + (G[i] + 2.0 * G23[i]));
+        }
+        t += dt;
+        ++steps;
+    }
+    return steps;
+}
+
+// B extended trajectories (socp_traj_var_batch): 16 lanes per trajectory
+template <int MODEL>
+__global__ void __launch_bounds__(128)
+traj_var_kernel(long B, int S, const double *__restrict__ mparams, const double *__restrict__ t0,
+                const double *__restrict__ tf, const double *__restrict__ X0, double *__restrict__ Xf,
+                unsigned long long *counter) {
+    typedef Model<MODEL> M;
+    constexpr int N = M::N, NV = N * (N + 1);
+    const long b = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+    const int i = threadIdx.x & 15;
+    int steps = 0;
+    if (b < B && i < N) {
+        typename M::Ctx c;
+        M::load(c, mparams + b * M::NP, nullptr);
+        double X[N], phi[N];
+#pragma unroll
+        for (int k = 0; k < N; ++k) { X[k] = X0[b * NV + k]; phi[k] = X0[b * NV + N * (k + 1) + i]; }
+        steps = var_traj_lane<MODEL>(c, X, phi, t0[b], tf[b], S);
+#pragma unroll
+        for (int k = 0; k < N; ++k) Xf[b * NV + N * (k + 1) + i] = phi[k];
+        if (i == 0) {
+#pragma unroll
+            for (int k = 0; k < N; ++k) Xf[b * NV + k] = X[k];
+        } else steps = 0;
+    }
+    count_steps(counter, steps);
+}
+
+// kernel 1': variational integration of every segment of the problems that asked for a Jacobian
+// (hybrj).  vends = D.jends reinterpreted: [problem][segment][N (N + 1)].
+template <int MODEL>
+__global__ void __launch_bounds__(128)
+integrate_var_worklist(SolverDev D, int cur) {
+    typedef Model<MODEL> M;
+    constexpr int N = M::N, NV = N * (N + 1);
+    const int njac = D.counts[cur * 2 + 1];
+    const int *jac_list = D.lists + (size_t)(cur * 2 + 1) * D.B;
+    const long total = (long)njac * D.M;
+    const int i = threadIdx.x & 15;
+    int steps = 0;
+    for (long w = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 4; w < total; w += ((long)gridDim.x * blockDim.x) >> 4) {
+        const long b = jac_list[w / D.M];
+        const int s = (int)(w % D.M);
+        if (i >= N) continue;
+        const double *xe = D.xe + b * D.P;
+        const int nm = N * D.M;
+        double t1, t2, sw[2] = {0.0227, 0.08};
+        timeline_pair(D, D.time + b * (D.M + 1), [&](int k) { return xe[nm + k]; }, s, t1, t2, sw);
+        typename M::Ctx c;
+        M::load(c, D.mparams + b * M::NP, sw);
+        double X[N], phi[N];
+#pragma unroll
+        for (int k = 0; k < N; ++k) { X[k] = xe[N * s + k]; phi[k] = (k == i) ? 1. : 0.; }
+        const int st = var_traj_lane<MODEL>(c, X, phi, t1, t2, D.S);
+        double *out = D.jends + ((size_t)b * D.M + s) * NV;
+#pragma unroll
+        for (int k = 0; k < N; ++k) out[N * (k + 1) + i] = phi[k];
+        if (i == 0) {
+#pragma unroll
+            for (int k = 0; k < N; ++k) out[k] = X[k];
+            steps += st;
+        }
+    }
+    count_steps(D.counters, steps);
+}
+
+// kernel 2a': shooting::ShootingFunctionJacobian (shooting.cpp:996-1130) from the segment sensitivities,
+// written column-major as StaticShootingFunctionJacobian transposes it (:889-893).  One thread per problem.
+template <int MODEL>
+__global__ void __launch_bounds__(128)
+assemble_jac_kernel(SolverDev D, int cur) {
+    typedef Model<MODEL> M;
+    typedef Variational<MODEL> V;
+    constexpr int N = M::N, n = M::DIM, NV = N * (N + 1);
+    const int njac = D.counts[cur * 2 + 1];
+    const int *jac_list = D.lists + (size_t)(cur * 2 + 1) * D.B;
+    const int P = D.P;
+    for (long w = (long)blockIdx.x * blockDim.x + threadIdx.x; w < njac; w += (long)gridDim.x * blockDim.x) {
+        const long b = jac_list[w];
+        const double *xe = D.xe + b * P;
+        const double *mp = D.mparams + b * M::NP;
+        double *J = D.fjac + (size_t)b * P * P;
+        auto put = [&](int row, int col, double v) { J[row + (size_t)col * P] = v; };     // dF_row / dx_col
+        for (int e = 0; e < P * P; ++e) J[e] = 0.;
+        double tl[SOCP_MAX_NODES + 1], sw[2] = {0.0227, 0.08};
+        const int nm = N * D.M;
+        timeline_all(D, D.time + b * (D.M + 1), [&](int k) { return xe[nm + k]; }, tl, sw);
+        typename M::Ctx c;
+        M::load(c, mp, sw);
+        int nbr = nm;
+        // rows of a boundary function: FIXED component j -> sensitivity row j, FREE -> row j + n; with a
+        // free time one more column (the flow) and one more row (dH) (model.hpp:104-120, :149-183)
+        auto boundary = [&](const double *Xs, const double *Phi, double t, const int *mode, bool identity, int row0, int col0,
+                            bool withH) {
+            double f[N], g[N + 1];
+            if (withH) { M::rhs(c, t, Xs, f); V::hgrad(Xs, g); }
+            for (int j = 0; j < n; ++j) {
+                const int r = (mode[j] == SOCP_FREE) ? j + n : j;
+                for (int q = 0; q < N; ++q) put(row0 + j, col0 + q, identity ? (q == r ? 1. : 0.) : Phi[N * r + q]);
+                if (withH) put(row0 + j, nbr, f[r]);
+            }
+            if (withH) {
+                for (int q = 0; q < N; ++q) {
+                    double acc = 0.;
+                    for (int k = 0; k < N; ++k) acc += g[k] * (identity ? (k == q ? 1. : 0.) : Phi[N * k + q]);
+                    put(nbr, col0 + q, acc);
+                }
+                double acc = 0.;
+                for (int k = 0; k < N; ++k) acc += g[k] * f[k];
+                put(nbr, nbr, acc + g[N]);
+            }
+        };
+        for (int i = 0; i < D.M; ++i) {
+            const double t2 = tl[i + 1];
+            const double *seg = D.jends + ((size_t)b * D.M + i) * NV;     // X(t2) and Phi = dX(t2)/dX(t1)
+            const double *Xtf = seg, *Phi = seg + N;                      // Phi[N k + q] = dX_k / dX0_q
+            const int index = N * (i + 1);
+            if (i == 0) {
+                const bool withH = D.mode_t[0] != SOCP_FIXED;
+                boundary(xe, nullptr, tl[0], D.mode_X[0], true, 0, 0, withH);
+                if (withH) nbr += 1;
+            }
+            if (i < D.M - 1) {
+                const double *Xp = xe + index;
+                const bool free_t = D.mode_t[i + 1] == SOCP_FREE;
+                double fxt[N], fxp[N];
+                M::rhs(c, t2, Xtf, fxt);
+                M::rhs(c, t2, Xp, fxp);
+                // shooting::MultipleShootingFunction(isJac = 1), shooting.cpp:1511-1576.  The derivative with
+                // respect to the free node time goes to that time's column -- and, as the reference copies a
+                // (4 dim + 1)-wide block (shooting.cpp:1063-1067), also to column index + N (a stray entry
+                // unless that IS the time column, as in the two-segment demo); reproduced for parity.
+                auto tcol = [&](int row, double v) { if (index + N < P) put(row, index + N, v); put(row, nbr, v); };
+                for (int j = 0; j < n; ++j) {
+                    const int m = D.mode_X[i + 1][j];
+                    if (m == SOCP_FIXED) {
+                        for (int q = 0; q < N; ++q) {
+                            put(index + j, index - N + q, Phi[N * j + q]);
+                            put(index + j + n, index + q, (q == j) ? 1. : 0.);
+                        }
+                        if (free_t) { tcol(index + j, fxt[j]); tcol(index + j + n, fxp[j]); }
+                    } else if (m == SOCP_CONTINUOUS) {
+                        for (int q = 0; q < N; ++q) {
+                            put(index + j, index - N + q, Phi[N * j + q]);
+                            put(index + j, index + q, (q == j) ? -1. : -0.);
+                            put(index + j + n, index - N + q, Phi[N * (j + n) + q]);
+                            put(index + j + n, index + q, (q == j + n) ? -1. : -0.);
+                        }
+                        if (free_t) { tcol(index + j, fxt[j] - fxp[j]); tcol(index + j + n, fxt[j + n] - fxp[j + n]); }
+                    }
+                }
+                if (free_t) {
+                    // model::SwitchingTimesFunction(isJac = 1), model.hpp:306-327
+                    double gX[N + 1], gP[N + 1];
+                    V::hgrad(Xtf, gX);
+                    V::hgrad(Xp, gP);
+                    for (int q = 0; q < N; ++q) {
+                        double a1 = 0., a2 = 0.;
+                        for (int k = 0; k < N; ++k) { a1 += gX[k] * Phi[N * k + q]; a2 -= gP[k] * ((k == q) ? 1. : 0.); }
+                        put(nbr, index - N + q, a1);
+                        put(nbr, index + q, a2);
+                    }
+                    double a = 0.;
+                    for (int k = 0; k < N; ++k) a += gX[k] * fxt[k] - gP[k] * fxp[k];
+                    put(nbr, nbr, a + (gX[N] - gP[N]));
+                    nbr += 1;
+                }
+            }
+            if (i == D.M - 1) {
+                const bool withH = D.mode_t[D.M] != SOCP_FIXED;
+                boundary(Xtf, Phi, t2, D.mode_X[D.M], false, n, N * i, withH);
+                if (withH) nbr += 1;
+            }
         }
     }
 }
@@ -1142,7 +1380,12 @@ hybrd_jac_kernel(SolverDev D, int cur, int per_group_doubles) {
                 for (int i = tid & 31; i < n; i += 32) W.q[i + (size_t)c * ldq_s] = gq[i + (size_t)c * n];
         gsync<G>();
         SOCP_PHASE(32, 0);
-        if (tid == 0) { is[I_NFEV] += n; is[I_JEVAL] = 1; atomicAdd(D.counters + 2, 1ULL); }
+        if (tid == 0) {
+            if (D.analytic) is[I_NJEV] += 1;               // hybrj counts Jacobian calls apart (njev)
+            else is[I_NFEV] += n;                          // hybrd: fdjac1 costs n residual evaluations
+            is[I_JEVAL] = 1;
+            atomicAdd(D.counters + 2, 1ULL);
+        }
         for (int i = tid; i < n; i += G) W.qtf[i] = W.fvec[i];
         // wa1 = rdiag, wa2 = acnorm
         int *hi = (int *)W.scr;                            // [n + 1] last non-zero row per column (scr is free here)
@@ -1204,7 +1447,7 @@ __global__ void solver_init(SolverDev D, const double *x_in, long first) {
 }
 
 __global__ void solver_finish(SolverDev D, long first, double *x_out, double *fvec_out, double *fjac_out,
-                              int *info, int *nfev, double *fnorm) {
+                              int *info, int *nfev, double *fnorm, int *njev) {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (x_out && i < D.B * D.P) x_out[first * D.P + i] = D.x[i];
     if (fvec_out && i < D.B * D.P) fvec_out[first * D.P + i] = D.fvec[i];
@@ -1214,6 +1457,7 @@ __global__ void solver_finish(SolverDev D, long first, double *x_out, double *fv
         // a problem still in flight when the round limit is hit reports info 2-like "not finished"
         if (info) info[first + i] = (is[I_PHASE] == PH_IDLE) ? is[I_INFO] : 2;
         if (nfev) nfev[first + i] = is[I_NFEV];
+        if (njev) njev[first + i] = is[I_NJEV];
         if (fnorm) fnorm[first + i] = D.dstate[i * D_COUNT + D_FNORM];
     }
 }

@@ -192,11 +192,22 @@ void launch_hybrd(socp_ctx *ctx, const SolverDev &D, int cur, int grid, int prof
     }
 }
 
+// hybrj: segment sensitivities and the analytic Jacobian for the problems in the Jacobian list
+template <int MODEL>
+typename std::enable_if<Variational<MODEL>::HAS>::type launch_variational(socp_ctx *ctx, const SolverDev &D, int cur, int grid) {
+    integrate_var_worklist<MODEL><<<grid, 128, 0, ctx->stream>>>(D, cur);
+    assemble_jac_kernel<MODEL><<<grid, 128, 0, ctx->stream>>>(D, cur);
+    ctx->launches += 2;
+}
+template <int MODEL>
+typename std::enable_if<!Variational<MODEL>::HAS>::type launch_variational(socp_ctx *, const SolverDev &, int, int) {}
+
 template <int MODEL>
 void launch_round(socp_ctx *ctx, const SolverDev &D, int cur, int grid_int, int grid_adv, int prof_slot) {
     if (prof_slot >= 0) cudaEventRecord(prof_event(ctx, kProfEv * prof_slot), ctx->stream);
     if (D.ode_tol > 0.) integrate_worklist<MODEL, true><<<grid_int, 128, 0, ctx->stream>>>(D, cur);
     else integrate_worklist<MODEL, false><<<grid_int, 128, 0, ctx->stream>>>(D, cur);
+    if (D.analytic) launch_variational<MODEL>(ctx, D, cur, grid_int);
     if (prof_slot >= 0) cudaEventRecord(prof_event(ctx, kProfEv * prof_slot + 1), ctx->stream);
     assemble_kernel<MODEL><<<grid_int, 128, 0, ctx->stream>>>(D, cur);
     if (prof_slot >= 0) cudaEventRecord(prof_event(ctx, kProfEv * prof_slot + 2), ctx->stream);
@@ -219,10 +230,14 @@ void launch_round_any(socp_ctx *ctx, const SolverDev &D, int cur, int gi, int ga
 // Run the state machine for B problems given DEVICE pointers; waves sized to the free memory.
 int run_solver(socp_ctx *ctx, const socp_shape *shape, long B, const double *d_mparams, const double *d_time,
                const double *d_Xb, const double *d_x_in, int run_mode, double xtol, int maxfev, double epsfcn,
-               double *d_x_out, double *d_fvec_out, double *d_fjac_out, int *d_info, int *d_nfev, double *d_fnorm) {
+               double *d_x_out, double *d_fvec_out, double *d_fjac_out, int *d_info, int *d_nfev, double *d_fnorm,
+               int analytic = 0, int *d_njev = nullptr) {
     HostPlan pl;
     int rc = make_plan(ctx, shape, pl);
     if (rc != SOCP_OK) return rc;
+    if (analytic && shape->model_id != SOCP_DOUBLE_INTEGRATOR)
+        return fail(ctx, SOCP_ERR_UNSUPPORTED, "analytic Jacobian (modelOrder 1): only the double integrator has variational equations, as in the reference");
+    pl.D.analytic = analytic;
     if (B == 0) return SOCP_OK;
     SolverDev &D = pl.D;
     // wave size from the memory that is free now plus what the workspace already holds
@@ -300,7 +315,7 @@ int run_solver(socp_ctx *ctx, const socp_shape *shape, long B, const double *d_m
             prof_harvest(ctx, pending);
         }
         const long nfin = std::max<long>(nthreads, d_fjac_out ? Bw * (long)D.P * D.P : 0);
-        solver_finish<<<(unsigned)((nfin + 255) / 256), 256, 0, ctx->stream>>>(D, first, d_x_out, d_fvec_out, d_fjac_out, d_info, d_nfev, d_fnorm);
+        solver_finish<<<(unsigned)((nfin + 255) / 256), 256, 0, ctx->stream>>>(D, first, d_x_out, d_fvec_out, d_fjac_out, d_info, d_nfev, d_fnorm, d_njev);
         ctx->launches += 1;
         CUDA_TRY(ctx, cudaGetLastError());
     }
@@ -387,6 +402,85 @@ int socp_solve_batch(socp_ctx *ctx, const socp_shape *shape, long B, const doubl
     if ((rc = fetch_out(ctx, info, d_info, (size_t)B, mem)) != SOCP_OK) return rc;
     if ((rc = fetch_out(ctx, nfev, d_nfev, (size_t)B, mem)) != SOCP_OK) return rc;
     if ((rc = fetch_out(ctx, fnorm, d_fn, (size_t)B, mem)) != SOCP_OK) return rc;
+    if (mem == SOCP_HOST) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return SOCP_OK;
+}
+
+int socp_solve_hybrj_batch(socp_ctx *ctx, const socp_shape *shape, long B, const double *mparams,
+                           const double *time, const double *Xb, double *x, double xtol, int maxfev,
+                           int *info, int *nfev, int *njev, double *fnorm, int mem) {
+    int rc = check_problem_args(ctx, shape, B, mparams, time, Xb, x, info);
+    if (rc != SOCP_OK) return rc;
+    if (xtol < 0. || maxfev <= 0) {
+        if (mem == SOCP_HOST) for (long b = 0; b < B; ++b) { info[b] = 0; if (nfev) nfev[b] = 0; if (njev) njev[b] = 0; }
+        return fail(ctx, SOCP_ERR_ARG, "xtol < 0 or maxfev <= 0");
+    }
+    if (B == 0) return SOCP_OK;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const int P = socp_num_param(shape), dim = kDim[shape->model_id], np = kNP[shape->model_id], M = shape->num_multi;
+    const double *d_mp = stage_in(ctx, SLOT_MPARAMS, mparams, (size_t)B * np, mem, &rc);
+    const double *d_time = stage_in(ctx, SLOT_TIME, time, (size_t)B * (M + 1), mem, &rc);
+    const double *d_Xb = stage_in(ctx, SLOT_XB, Xb, (size_t)B * (M + 1) * dim, mem, &rc);
+    const double *d_xin = stage_in(ctx, SLOT_X, (const double *)x, (size_t)B * P, mem, &rc);
+    double *d_x = (mem == SOCP_DEVICE) ? x : (double *)d_xin;
+    int *d_info = stage_out(ctx, SLOT_INFO, info, (size_t)B, mem, &rc);
+    int *d_nfev = stage_out(ctx, SLOT_NFEV, nfev, (size_t)B, mem, &rc);
+    int *d_njev = stage_out(ctx, SLOT_AUX0, njev, (size_t)B, mem, &rc);
+    double *d_fn = stage_out(ctx, SLOT_FNORM, fnorm, (size_t)B, mem, &rc);
+    if (rc != SOCP_OK) return rc;
+    rc = run_solver(ctx, shape, B, d_mp, d_time, d_Xb, d_xin, RUN_SOLVE, xtol, maxfev, 1e-15, d_x, nullptr, nullptr, d_info, d_nfev, d_fn, 1, d_njev);
+    if (rc != SOCP_OK) return rc;
+    if ((rc = fetch_out(ctx, x, d_x, (size_t)B * P, mem)) != SOCP_OK) return rc;
+    if ((rc = fetch_out(ctx, info, d_info, (size_t)B, mem)) != SOCP_OK) return rc;
+    if ((rc = fetch_out(ctx, nfev, d_nfev, (size_t)B, mem)) != SOCP_OK) return rc;
+    if ((rc = fetch_out(ctx, njev, d_njev, (size_t)B, mem)) != SOCP_OK) return rc;
+    if ((rc = fetch_out(ctx, fnorm, d_fn, (size_t)B, mem)) != SOCP_OK) return rc;
+    if (mem == SOCP_HOST) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return SOCP_OK;
+}
+
+int socp_jacobian_batch(socp_ctx *ctx, const socp_shape *shape, long B, const double *mparams,
+                        const double *time, const double *Xb, const double *x, double *fjac, int mem) {
+    int rc = check_problem_args(ctx, shape, B, mparams, time, Xb, x, fjac);
+    if (rc != SOCP_OK || B == 0) return rc;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const int P = socp_num_param(shape), dim = kDim[shape->model_id], np = kNP[shape->model_id], M = shape->num_multi;
+    const double *d_mp = stage_in(ctx, SLOT_MPARAMS, mparams, (size_t)B * np, mem, &rc);
+    const double *d_time = stage_in(ctx, SLOT_TIME, time, (size_t)B * (M + 1), mem, &rc);
+    const double *d_Xb = stage_in(ctx, SLOT_XB, Xb, (size_t)B * (M + 1) * dim, mem, &rc);
+    const double *d_x = stage_in(ctx, SLOT_X, x, (size_t)B * P, mem, &rc);
+    double *d_j = stage_out(ctx, SLOT_FJAC, fjac, (size_t)B * P * P, mem, &rc);
+    if (rc != SOCP_OK) return rc;
+    rc = run_solver(ctx, shape, B, d_mp, d_time, d_Xb, d_x, RUN_FDJAC, 0., 1, 1e-15, nullptr, nullptr, d_j, nullptr, nullptr, nullptr, 1, nullptr);
+    if (rc != SOCP_OK) return rc;
+    if ((rc = fetch_out(ctx, fjac, d_j, (size_t)B * P * P, mem)) != SOCP_OK) return rc;
+    if (mem == SOCP_HOST) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return SOCP_OK;
+}
+
+int socp_traj_var_batch(socp_ctx *ctx, int model_id, int step_nbr, long B, const double *mparams,
+                        const double *t0, const double *tf, const double *X0, double *Xf, int mem) {
+    if (!ctx) return SOCP_ERR_ARG;
+    if (model_id < 0 || model_id >= SOCP_NUM_MODELS || B < 0 || !mparams || !t0 || !tf || !X0 || !Xf)
+        return fail(ctx, SOCP_ERR_ARG, "socp_traj_var_batch: bad arguments");
+    if (model_id != SOCP_DOUBLE_INTEGRATOR)
+        return fail(ctx, SOCP_ERR_UNSUPPORTED, "variational integration: only the double integrator implements it, as in the reference");
+    if (B == 0) return SOCP_OK;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const int N = 2 * kDim[model_id], NV = N * (N + 1), np = kNP[model_id];
+    const int S = step_nbr > 0 ? step_nbr : kSteps[model_id];
+    int rc = SOCP_OK;
+    const double *d_mp = stage_in(ctx, SLOT_MPARAMS, mparams, (size_t)B * np, mem, &rc);
+    const double *d_t0 = stage_in(ctx, SLOT_T0, t0, (size_t)B, mem, &rc);
+    const double *d_tf = stage_in(ctx, SLOT_TF, tf, (size_t)B, mem, &rc);
+    const double *d_X0 = stage_in(ctx, SLOT_X0, X0, (size_t)B * NV, mem, &rc);
+    double *d_Xf = stage_out(ctx, SLOT_XF, Xf, (size_t)B * NV, mem, &rc);
+    if (rc != SOCP_OK) return rc;
+    const long threads = B * 16;
+    traj_var_kernel<DOUBLE_INTEGRATOR><<<(unsigned)((threads + 127) / 128), 128, 0, ctx->stream>>>(B, S, d_mp, d_t0, d_tf, d_X0, d_Xf, ctx->d_counters);
+    ctx->launches += 1;
+    CUDA_TRY(ctx, cudaGetLastError());
+    if ((rc = fetch_out(ctx, Xf, d_Xf, (size_t)B * NV, mem)) != SOCP_OK) return rc;
     if (mem == SOCP_HOST) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return SOCP_OK;
 }

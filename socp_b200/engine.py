@@ -305,6 +305,43 @@ class Engine:
                                              a.out(nfev), a.out(fnorm), mem))
         return dict(x=x, info=info, nfev=nfev, fnorm=fnorm)
 
+    # -- analytic-Jacobian path (modelOrder == 1; the double integrator, as in the reference) -----
+    def traj_var_batch(self, model_id, mparams, t0, X0, tf, step_nbr=0):
+        """model::ComputeTraj(isJac = 1) for B extended states [(2dim+1) 2dim] (host arrays)."""
+        X0 = np.ascontiguousarray(X0, dtype=np.float64)
+        B = X0.shape[0]
+        mparams = self._bcast_params(mparams, B, model_nparams(model_id))
+        t0 = np.broadcast_to(np.asarray(t0, dtype=np.float64), (B,))
+        tf = np.broadcast_to(np.asarray(tf, dtype=np.float64), (B,))
+        out = np.empty_like(X0)
+        a = _Arg(HOST)
+        self._check(self._L.socp_traj_var_batch(self._h, model_id, int(step_nbr or 0), B, a.inp(mparams), a.inp(t0),
+                                                a.inp(tf), a.inp(X0), a.out(out), HOST))
+        return out
+
+    def jacobian_batch(self, shape, mparams, time, Xb, x):
+        """shooting::ShootingFunctionJacobian; returns [B][P][P] with J[b, i, j] = dF_i/dx_j (host arrays)."""
+        mem, B, mparams = self._problem_args(shape, mparams, time, Xb, x)
+        P = num_param(shape)
+        buf = np.empty((B, P * P))
+        a = _Arg(HOST)
+        self._check(self._L.socp_jacobian_batch(self._h, ctypes.byref(shape), B, a.inp(mparams), a.inp(time),
+                                                a.inp(Xb), a.inp(x), a.out(buf), HOST))
+        return buf.reshape(B, P, P).transpose(0, 2, 1).copy()
+
+    def solve_hybrj_batch(self, shape, mparams, time, Xb, x, xtol=1e-8, maxfev=10000):
+        """shooting::SolveShootingFunction with modelOrder == 1 (hybrj); x updated in place (host arrays)."""
+        mem, B, mparams = self._problem_args(shape, mparams, time, Xb, x)
+        if not (isinstance(x, np.ndarray) and x.dtype == np.float64 and x.flags["C_CONTIGUOUS"]):
+            raise ValueError("x must be a contiguous float64 array (updated in place)")
+        info, nfev, njev = (np.empty(B, dtype=np.int32) for _ in range(3))
+        fnorm = np.empty(B)
+        a = _Arg(HOST)
+        self._check(self._L.socp_solve_hybrj_batch(self._h, ctypes.byref(shape), B, a.inp(mparams), a.inp(time),
+                                                   a.inp(Xb), a.out(x), float(xtol), int(maxfev), a.out(info),
+                                                   a.out(nfev), a.out(njev), a.out(fnorm), HOST))
+        return dict(x=x, info=info, nfev=nfev, njev=njev, fnorm=fnorm)
+
     def continuation_param_batch(self, shape, mparams, time, Xb, x, step, param_idx, goal, xtol=1e-8,
                                  maxfev=10000, step_min=1e-12):
         """shooting::SolveShootingContinuation(step, Rdata, Rgoal) for B problems (host arrays)."""

@@ -106,7 +106,7 @@ def test_double_integrator_demo_matches_reference():
     (`modelOrder = 0` row): nfev 82 / 25 / 151."""
     assert os.access(os.path.join(BIN, "demo_double_integrator"), os.X_OK), "run __graft_entry__.build() first"
     out = _run("demo_double_integrator")
-    rows = re.findall(r"stage (\d) info (\d+) nfev (\d+) tf (\S+) p0 (.*)", out)
+    rows = re.findall(r"stage (\d) info (\d+) nfev (\d+) njev \d+ tf (\S+) p0 (.*)", out)
     assert len(rows) == 3, out
     want = [(82, 27.655974527562908, [-0.0056730204147606, -0.0085095306215938124]),
             (25, 30.80070288243714, [-0.0041067603843020425, -0.0082135207686335095]),
@@ -116,6 +116,19 @@ def test_double_integrator_demo_matches_reference():
         assert int(info) == 1 and int(nfev) == w_nfev, (stage, info, nfev)
         assert abs(float(tf) - w_tf) <= 1e-8 * w_tf
         assert abs(p[0] - w_p[0]) <= 1e-7 * abs(w_p[0]) and abs(p[1] - w_p[1]) <= 1e-7 * abs(w_p[1])
+
+
+@pytest.mark.gpu
+def test_double_integrator_demo_hybrj_matches_reference():
+    """The same three stages with modelOrder = 1, as tests/testDoubleIntegrator.cpp runs them: analytic
+    Jacobian + hybrj.  Reference: nfev/njev 30/4, 12/1, 125/2."""
+    out = _run("demo_double_integrator", "1")
+    rows = re.findall(r"stage (\d) info (\d+) nfev (\d+) njev (\d+) tf (\S+) p0", out)
+    assert len(rows) == 3, out
+    want = [(30, 4, 27.655974527562883), (12, 1, 30.800702882437143), (125, 2, 25.900200641161657)]
+    for (stage, info, nfev, njev, tf), (w_nfev, w_njev, w_tf) in zip(rows, want):
+        assert int(info) == 1 and (int(nfev), int(njev)) == (w_nfev, w_njev), (stage, info, nfev, njev)
+        assert abs(float(tf) - w_tf) <= 1e-8 * w_tf
 
 
 @pytest.mark.gpu
