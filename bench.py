@@ -41,7 +41,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=100000, help="problems per GPU")
     ap.add_argument("--e2e-steps", type=int, default=2)
-    ap.add_argument("--cpu-sample", type=int, default=0, help="problems in the CPU baseline sample (0 = 4 per core)")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="problems in the CPU baseline sample (0 = 16 per core, about 10 s of CPU work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -173,7 +173,7 @@ def run_reference(args, rank):
     import scenarios as S
     from backends import OracleBackend
     pool = CpuPool()
-    per_step = args.cpu_sample or 4 * pool.cores
+    per_step = args.cpu_sample or 8 * pool.cores
     n = per_step * (args.steps + args.warmup)
     # build the same problems as the GPU arm (same seed); the guess integration runs on the CPU port
     ora = OracleBackend()
@@ -386,7 +386,7 @@ def main():
 
     cpu_baseline = None
     if pool is not None:
-        n_s = args.cpu_sample or 4 * pool.cores
+        n_s = args.cpu_sample or 16 * pool.cores
         specs = [spec_of(k, mp, time_, Xb, x0) for k in range(n_s)]
         dt, res = pool.solve(specs)
         pool.close()

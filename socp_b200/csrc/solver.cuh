@@ -275,7 +275,10 @@ integrate_worklist(SolverDev D, int cur) {
 // their forward difference is exactly zero, as in the reference.
 template <int MODEL>
 __device__ __noinline__ void assemble(const SolverDev &D, long b, int col, double h, const double *base_ends,
-                                      const double *jends_b, double *out) {
+                                      const double *jends_b, double *out, int seg_lo, int seg_hi) {
+    // Only the segments seg_lo..seg_hi are evaluated (the caller knows which ones a perturbed unknown can
+    // reach and pre-loads `out` with the base residual, so every other entry differences to an exact zero,
+    // as in the reference); the free-time row counter still runs over all of them.
     auto emit = [&](int i, double v) { out[i] = v; };
     typedef Model<MODEL> M;
     constexpr int N = M::N, n = M::DIM;
@@ -299,6 +302,12 @@ __device__ __noinline__ void assemble(const SolverDev &D, long b, int col, doubl
     int nbr = nm;
     double X1[N], Xtf[N], Xp[N];
     for (int i = 0; i < D.M; ++i) {
+        if (i < seg_lo || i > seg_hi) {
+            if (i == 0 && D.mode_t[0] != SOCP_FIXED) nbr += 1;
+            if (i < D.M - 1 && D.mode_t[i + 1] == SOCP_FREE) nbr += 1;
+            if (i == D.M - 1 && D.mode_t[D.M] != SOCP_FIXED) nbr += 1;
+            continue;
+        }
         const double t2 = tl[i + 1];
         const double *e = rec(i);
 #pragma unroll
@@ -397,7 +406,7 @@ assemble_kernel(SolverDev D, int cur) {
             const int trial = 1 - is[I_BASE];
             const double *te = D.ends + ((b * 2 + trial) * D.M) * D.REC;
             double *out = (is[I_PHASE] == PH_F0) ? D.fvec + b * n : D.wa4 + b * n;
-            assemble<MODEL>(D, b, -1, 0.0, te, D.jends + (size_t)b * D.nJ * D.REC, out);
+            assemble<MODEL>(D, b, -1, 0.0, te, D.jends + (size_t)b * D.nJ * D.REC, out, 0, D.M - 1);
         } else {
             const long w2 = w - nres;
             const long b = jac_list[w2 / n];
@@ -407,7 +416,13 @@ assemble_kernel(SolverDev D, int cur) {
             const double h = fd_step(D.xe[b * n + j], D.epsfcn);
             double *colj = D.fjac + (size_t)b * n * n + (size_t)j * n;
             const double *fvec = D.fvec + b * n;
-            assemble<MODEL>(D, b, j, h, be, D.jends + (size_t)b * D.nJ * D.REC, colj);
+            // an unknown of node s enters segment s - 1 (as the right-hand state of its continuity rows) and
+            // segment s (as its start point); a free time moves every segment
+            const int N2 = 2 * Model<MODEL>::DIM, node = j / N2;
+            const bool state_col = j < N2 * D.M;
+            for (int i = 0; i < n; ++i) colj[i] = fvec[i];
+            assemble<MODEL>(D, b, j, h, be, D.jends + (size_t)b * D.nJ * D.REC, colj,
+                            state_col ? max(node - 1, 0) : 0, state_col ? node : D.M - 1);
             for (int i = 0; i < n; ++i) colj[i] = (colj[i] - fvec[i]) / h;      // fdjac1
         }
     }
