@@ -30,6 +30,10 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 FLOPS_PER_RK4_STEP = {"goddard": 1100.0}     # SURVEY.md 8(d) / BASELINE.md section 3 (nominal count)
+# DRAM traffic of hybrd_res_kernel per Broyden iteration of one problem, from the `ncu --set full` capture
+# profiles/r1_final_ncu_res_raw.csv: (dram__bytes_read.sum + dram__bytes_write.sum) = 688.1 MB for the 3678
+# iterations of the captured launch (1.03x the algorithmic 182 KB: no wasted re-reads)
+NCU_DRAM_BYTES_PER_ITERATION = 688.148e6 / 3678
 METRIC = "shooting solves/sec (Goddard free-tf, M=6, P=85; RK4 steps/sec and % of FP64 roofline alongside)"
 
 
@@ -322,7 +326,12 @@ def main():
     d = kern[dom]
     n_launch = max(st["solver_rounds"], 1.0)
     roofline = {"kernel": dom, "bound": d["bound"], "achieved": d["achieved"], "peak": d["peak"], "unit": d["unit"],
-                "frac": d["frac"], "traffic": None, "avg_launch_ms": d["ms"] / n_launch, "launches": n_launch,
+                "frac": d["frac"],
+                "traffic": (NCU_DRAM_BYTES_PER_ITERATION * st["iterations"] / n_launch) if dom == "hybrd_res_kernel" else None,
+                "traffic_note": "bytes per launch = ncu-measured DRAM bytes per problem-iteration (profiles/r1_final_ncu_res_raw.csv) "
+                                "x problem-iterations per launch of this run",
+                "algorithmic_bytes_per_launch": bytes_iter * st["iterations"] / n_launch,
+                "avg_launch_ms": d["ms"] / n_launch, "launches": n_launch,
                 "share_of_step": d["share_of_step"],
                 "algorithmic_bytes_per_problem_iteration": bytes_iter,
                 "problem_iterations": st["iterations"], "jacobian_factorisations": st["jac_evals"],
