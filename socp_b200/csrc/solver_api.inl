@@ -130,6 +130,7 @@ struct SmemPlan {
     int G;                               // threads per problem: one warp, or a 128-thread CTA
     int groups;                          // problems per CTA (G == 32 only)
     bool stage_r, stage_q_jac;
+    bool jac_r_global;                   // Jacobian phase: leave R in global memory when that fits one more CTA per SM
     int doubles_res, doubles_jac;        // shared doubles per group
     size_t bytes_res, bytes_jac;         // per CTA
 };
@@ -157,6 +158,12 @@ SmemPlan smem_plan(const SolverDev &D) {
     }
     p.bytes_res = dr * 8 * p.groups;
     p.bytes_jac = dj * 8 * p.groups;
+    // In the Jacobian phase R is written once (pack_r) and read by one dogleg, while Q is swept 2 P times:
+    // if dropping R from shared memory lets one more CTA live on the SM, do that (P = 85: 96 -> 67 KB,
+    // 2 -> 3 CTAs/SM, measured -25 % kernel time)
+    const size_t sm_bytes = 227 * 1024;
+    p.jac_r_global = p.G == 128 && p.stage_q_jac &&
+                     sm_bytes / ((dj - D.LR) * 8 + 1024) > sm_bytes / (dj * 8 + 1024);
     return p;
 }
 
@@ -186,7 +193,9 @@ void launch_hybrd(socp_ctx *ctx, const SolverDev &D, int cur, int grid, int prof
         if (sp.stage_r) launch_smem(hybrd_res_kernel<128, true>, g, thr, sp.bytes_res, ctx->stream, D, cur, sp.doubles_res);
         else launch_smem(hybrd_res_kernel<128, false>, g, thr, sp.bytes_res, ctx->stream, D, cur, sp.doubles_res);
         if (prof_slot >= 0) cudaEventRecord(prof_event(ctx, kProfEv * prof_slot + 3), ctx->stream);
-        if (sp.stage_q_jac) launch_smem(hybrd_jac_kernel<128, true, true>, g, thr, sp.bytes_jac, ctx->stream, D, cur, sp.doubles_jac);
+        if (sp.stage_q_jac && sp.jac_r_global)          // R straight to global memory: one more CTA per SM
+            launch_smem(hybrd_jac_kernel<128, false, true>, g, thr, (size_t)(sp.doubles_jac - D.LR) * 8, ctx->stream, D, cur, sp.doubles_jac - D.LR);
+        else if (sp.stage_q_jac) launch_smem(hybrd_jac_kernel<128, true, true>, g, thr, sp.bytes_jac, ctx->stream, D, cur, sp.doubles_jac);
         else if (sp.stage_r) launch_smem(hybrd_jac_kernel<128, true, false>, g, thr, sp.bytes_jac, ctx->stream, D, cur, sp.doubles_jac);
         else launch_smem(hybrd_jac_kernel<128, false, false>, g, thr, sp.bytes_jac, ctx->stream, D, cur, sp.doubles_jac);
     }

@@ -1,4 +1,5 @@
 #!/bin/bash
+# A/B runs of bench.py (1 timed step) under environment overrides; prints one summary line per variant
 O=gpurun_out/ab; mkdir -p $O
 run() { name=$1; shift; env "$@" timeout 300 python bench.py --no-cpu-baseline --steps 1 --warmup 1 --e2e-steps 1 > $O/$name.json 2> $O/$name.err; python - $O/$name.json $name <<'PY'
 import json,sys
@@ -9,9 +10,5 @@ PY
 for v in "$@"; do
   case $v in
     base) run base X=1;;
-    oldjac) run oldjac SOCP_JAC_OLD=1;;
-    warp4) run warp4 SOCP_RES_WARP=4;;
-    warp2) run warp2 SOCP_RES_WARP=2;;
-    warp1) run warp1 SOCP_RES_WARP=1;;
   esac
 done
