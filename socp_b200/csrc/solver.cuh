@@ -275,11 +275,12 @@ integrate_worklist(SolverDev D, int cur) {
 // their forward difference is exactly zero, as in the reference.
 template <int MODEL>
 __device__ __noinline__ void assemble(const SolverDev &D, long b, int col, double h, const double *base_ends,
-                                      const double *jends_b, double *out, int seg_lo, int seg_hi) {
+                                      const double *jends_b, double *out, int seg_lo, int seg_hi, const double *base) {
     // Only the segments seg_lo..seg_hi are evaluated (the caller knows which ones a perturbed unknown can
-    // reach and pre-loads `out` with the base residual, so every other entry differences to an exact zero,
-    // as in the reference); the free-time row counter still runs over all of them.
-    auto emit = [&](int i, double v) { out[i] = v; };
+    // reach; every other entry of a forward-difference column is an exact zero, as in the reference, and the
+    // column was zero-filled beforehand); the free-time row counter still runs over all of them.
+    // base != nullptr: emit the forward difference (F_i(x + h e_col) - base_i) / h instead of F_i.
+    auto emit = [&](int i, double v) { out[i] = base ? (v - base[i]) / h : v; };
     typedef Model<MODEL> M;
     constexpr int N = M::N, n = M::DIM;
     const double *xe = D.xe + b * D.P;
@@ -388,6 +389,16 @@ __device__ __noinline__ void assemble(const SolverDev &D, long b, int col, doubl
     }
 }
 
+// ---- kernel 2a0: zero the Jacobians about to be assembled (coalesced; the column threads of
+// assemble_kernel then write only the rows a perturbed unknown can reach) -----------------------------
+__global__ void __launch_bounds__(256) zero_fjac_kernel(SolverDev D, int cur) {
+    const int njac = D.analytic ? 0 : D.counts[cur * 2 + 1];
+    const int *jac_list = D.lists + (size_t)(cur * 2 + 1) * D.B;
+    const long pp = (long)D.P * D.P;
+    for (long w = (long)blockIdx.x * blockDim.x + threadIdx.x; w < (long)njac * pp; w += (long)gridDim.x * blockDim.x)
+        D.fjac[(size_t)jac_list[w / pp] * pp + (w % pp)] = 0.;
+}
+
 // ---- kernel 2a: assemble residuals and forward-difference Jacobian columns ----------------------
 // One thread per residual request, one thread per (Jacobian request, column).  This is the only
 // solver kernel besides integrate_worklist that contains model code.
@@ -406,7 +417,7 @@ assemble_kernel(SolverDev D, int cur) {
             const int trial = 1 - is[I_BASE];
             const double *te = D.ends + ((b * 2 + trial) * D.M) * D.REC;
             double *out = (is[I_PHASE] == PH_F0) ? D.fvec + b * n : D.wa4 + b * n;
-            assemble<MODEL>(D, b, -1, 0.0, te, D.jends + (size_t)b * D.nJ * D.REC, out, 0, D.M - 1);
+            assemble<MODEL>(D, b, -1, 0.0, te, D.jends + (size_t)b * D.nJ * D.REC, out, 0, D.M - 1, nullptr);
         } else {
             const long w2 = w - nres;
             const long b = jac_list[w2 / n];
@@ -420,10 +431,9 @@ assemble_kernel(SolverDev D, int cur) {
             // segment s (as its start point); a free time moves every segment
             const int N2 = 2 * Model<MODEL>::DIM, node = j / N2;
             const bool state_col = j < N2 * D.M;
-            for (int i = 0; i < n; ++i) colj[i] = fvec[i];
+            // fdjac1: the column was zero-filled (zero_fjac_kernel); only the reachable rows are written
             assemble<MODEL>(D, b, j, h, be, D.jends + (size_t)b * D.nJ * D.REC, colj,
-                            state_col ? max(node - 1, 0) : 0, state_col ? node : D.M - 1);
-            for (int i = 0; i < n; ++i) colj[i] = (colj[i] - fvec[i]) / h;      // fdjac1
+                            state_col ? max(node - 1, 0) : 0, state_col ? node : D.M - 1, fvec);
         }
     }
 }

@@ -218,6 +218,7 @@ void launch_round(socp_ctx *ctx, const SolverDev &D, int cur, int grid_int, int 
     else integrate_worklist<MODEL, false><<<grid_int, 128, 0, ctx->stream>>>(D, cur);
     if (D.analytic) launch_variational<MODEL>(ctx, D, cur, grid_int);
     if (prof_slot >= 0) cudaEventRecord(prof_event(ctx, kProfEv * prof_slot + 1), ctx->stream);
+    if (!D.analytic) { zero_fjac_kernel<<<grid_int, 256, 0, ctx->stream>>>(D, cur); ctx->launches += 1; }
     assemble_kernel<MODEL><<<grid_int, 128, 0, ctx->stream>>>(D, cur);
     if (prof_slot >= 0) cudaEventRecord(prof_event(ctx, kProfEv * prof_slot + 2), ctx->stream);
     launch_hybrd(ctx, D, cur, grid_adv, prof_slot);
