@@ -859,6 +859,28 @@ __device__ void dogleg_g(int n, const double *r, const double *diag, const doubl
     }
     gsync<G>();
     if ((tid >> 5) == seqw) {
+        if (n <= 96) {
+            // every lane keeps the running right-hand sides of its rows i = lane, lane + 32, lane + 64 in
+            // registers; per step: corrected quotient in the owner lane, one shuffle, three predicated FMAs
+            double b0 = (lane < n) ? x[lane] : 0., b1 = (lane + 32 < n) ? x[lane + 32] : 0., b2 = (lane + 64 < n) ? x[lane + 64] : 0.;
+            // p_k: index of R(i_k, j) in the packed rows, moves one to the left per step
+            int p0 = rowstart(n, lane) + (n - 1 - lane), p1 = rowstart(n, lane + 32) + (n - 1 - lane - 32),
+                p2 = rowstart(n, lane + 64) + (n - 1 - lane - 64);
+            for (int j = n - 1; j >= 0; --j) {
+                const int slot = j >> 5;
+                const double bj = (slot == 0) ? b0 : (slot == 1) ? b1 : b2;
+                const double d = wa2[j], dinv = wa1[j];
+                const double q0 = bj * dinv;
+                const double xj = __shfl_sync(0xffffffffu, fma(fma(-q0, d, bj), dinv, q0), j & 31);
+                const double r0 = (lane < j) ? r[p0] : 0., r1 = (lane + 32 < j) ? r[p1] : 0., r2 = (lane + 64 < j) ? r[p2] : 0.;
+                b0 = fma(-r0, xj, b0); b1 = fma(-r1, xj, b1); b2 = fma(-r2, xj, b2);
+                if (lane == (j & 31)) { if (slot == 0) b0 = xj; else if (slot == 1) b1 = xj; else b2 = xj; }
+                --p0; --p1; --p2;
+            }
+            if (lane < n) x[lane] = b0;
+            if (lane + 32 < n) x[lane + 32] = b1;
+            if (lane + 64 < n) x[lane + 64] = b2;
+        } else {
         double bj = x[n - 1];                                  // rhs of the pivot row (owner lane)
         for (int j = n - 1; j >= 0; --j) {
             const int owner = j & 31, next_owner = (j - 1) & 31;
@@ -871,6 +893,7 @@ __device__ void dogleg_g(int n, const double *r, const double *diag, const doubl
             if (lane == owner) x[j] = xj;
             if (j > 0 && lane == next_owner) { bj = cx - cr * xj; x[j - 1] = bj; }
             for (int i = lane; i < j - 1; i += 32) x[i] -= r[rowstart(n, i) + (j - i)] * xj;
+        }
         }
     }
     gsync<G>();
@@ -1035,6 +1058,45 @@ __device__ void r1updt_g(int n, double *s, const double *u, double *v, double *w
     // sequential in j.  Warp 0: each lane owns the columns i = lane (mod 32) for the whole sweep (no
     // barrier inside the loop); the pivot w[j+1] is carried in a register and broadcast by one shuffle.
     if ((tid >> 5) == seqw) {
+        if (n <= 96) {
+            // w lives in registers (three slots per lane: i = lane, lane + 32, lane + 64); row j of s is read
+            // and written once; everything is predicated (no divergent branch in the step) and the pivot
+            // for the next step is picked from the right slot and broadcast by one shuffle
+            double w0 = (lane < n) ? w[lane] : 0., w1 = (lane + 32 < n) ? w[lane + 32] : 0., w2 = (lane + 64 < n) ? w[lane + 64] : 0.;
+            double wj = __shfl_sync(FULL, w0, 0);
+            double sjj = s[0];
+            int jj = 0;                                            // rowstart(n, j)
+            for (int j = 0; j < n - 1; ++j) {
+                const int i0 = lane, i1 = lane + 32, i2 = lane + 64;
+                const bool a0 = i0 > j && i0 < n, a1 = i1 > j && i1 < n, a2 = i2 > j && i2 < n;
+                const double s0 = a0 ? s[jj + (i0 - j)] : 0., s1 = a1 ? s[jj + (i1 - j)] : 0., s2 = a2 ? s[jj + (i2 - j)] : 0.;
+                const int jjn = jj + (n - j);
+                const double sjj_next = s[jjn];
+                double c = 1., sgl = 0.;
+                const bool rot = wj != 0.;                         // uniform
+                if (rot) givens(sjj, wj, c, sgl);
+                if (rot) {
+                    if (a0) s[jj + (i0 - j)] = fma(c, s0, sgl * w0);
+                    if (a1) s[jj + (i1 - j)] = fma(c, s1, sgl * w1);
+                    if (a2) s[jj + (i2 - j)] = fma(c, s2, sgl * w2);
+                    if (a0) w0 = fma(c, w0, -sgl * s0);
+                    if (a1) w1 = fma(c, w1, -sgl * s1);
+                    if (a2) w2 = fma(c, w2, -sgl * s2);
+                }
+                if (lane == (j & 31)) {
+                    if (rot) { s[jj] = fma(c, sjj, sgl * wj); cs[j] = c; sn[j] = sgl; }
+                    tmp[j] = rot ? ((fabs(sjj) < fabs(wj)) ? 1. : 0.) : 2.;
+                }
+                const int slot = (j + 1) >> 5;
+                const double pick = (slot == 0) ? w0 : (slot == 1) ? w1 : w2;
+                wj = __shfl_sync(FULL, pick, (j + 1) & 31);
+                sjj = sjj_next;
+                jj = jjn;
+            }
+            // w[j] for j < n - 1 is replaced by tau below; only the last entry keeps its value
+            if (lane == ((n - 1) & 31)) w[n - 1] = ((n - 1) >> 5) == 0 ? w0 : ((n - 1) >> 5) == 1 ? w1 : w2;
+            for (int j = lane; j < n - 1; j += 32) if (tmp[j] == 2.) w[j] = 0.;
+        } else {
         double wj = w[0];
         double sjj = s[0];
         for (int j = 0; j < n - 1; ++j) {
@@ -1062,6 +1124,7 @@ __device__ void r1updt_g(int n, double *s, const double *u, double *v, double *w
             else if (lane == (j & 31)) tmp[j] = 2.;                 // no rotation: w[j] stays zero
             wj = __shfl_sync(FULL, carry, nown);
             sjj = sjj_next;
+        }
         }
         // MINPACK's tau for r1mpyq (one divide each, off the sequential chain); entries written by this lane
         for (int j = lane; j < n - 1; j += 32) {
