@@ -118,3 +118,35 @@ def test_hybrj_two_segments_matches_reference(oracle_lib):
     assert s.call_number() == (o["nfev"], o["njev"])
     if info == 1:
         assert np.array_equal(s.params(), o["x"])
+
+
+def _golden_hybrj():
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_hybrj.json")) as f:
+        return json.load(f)
+
+
+def _unhex(v):
+    return np.array([float.fromhex(s) for s in v])
+
+
+def test_oracle_matches_golden_hybrj(oracle_lib):
+    """The committed vectors (tests/golden/golden_hybrj.json, recorded from the unmodified reference by
+    tests/golden/make_golden_hybrj.py) pin the oracle where the reference build is not available."""
+    g = _golden_hybrj()
+    p = OracleBackend().problem(S.di_problem())
+    for e in g["traj_var"]:
+        assert np.array_equal(p.traj_var(0.0, _unhex(e["X0"]), float.fromhex(e["tf"])), _unhex(e["Xf"]))
+    for e, make in zip(g["jacobian"], (S.di_problem, di_wp_spec)):
+        spec = make()
+        x = _unhex(e["x"])
+        J = OracleBackend().problem(spec).jacobian(x)
+        assert np.array_equal(J.reshape(-1), _unhex(e["J"]))
+    for e, make in zip(g["solve"], (S.di_problem, di_wp_spec)):
+        spec = make()
+        o = OracleBackend().problem(spec).solve_hybrj(spec["x0"], xtol=spec["xtol"])
+        assert (o["info"], o["nfev"], o["njev"]) == (e["info"], e["nfev"], e["njev"])
+        if e["info"] == 1:          # (SOCP keeps tab_param unchanged when the solve fails, shooting.cpp:588)
+            assert np.array_equal(o["x"], _unhex(e["x"]))
+    assert (g["solve"][0]["nfev"], g["solve"][0]["njev"]) == (30, 4)
