@@ -77,7 +77,8 @@ def test_init_analytical_matches_reference(built):
         mp[13] = mu_gft
         ref = pyref.RefModel(S.INTERCEPTOR, model_order=0, step_nbr=0)
         ref.set("mu_gft", mu_gft)
-        assert np.allclose(ref.params(), mp)
+        keep = [k for k in range(17) if k not in (11, 12)]        # r_2p, t_2p: never initialised by the reference's constructor
+        assert np.allclose(ref.params()[keep], mp[keep])
         for Xi, Xf in cases:
             a = np.r_[Xi, np.zeros(6)]
             b = np.r_[Xf, np.zeros(6)]
