@@ -55,8 +55,10 @@ def test_bad_arguments_are_refused():
         eng.traj_batch(7, mp, 0.0, np.zeros((1, 12)), 1.0)                       # unknown model id
     bad = shape_of(spec)
     bad.num_multi = 0
-    with pytest.raises(sb.SocpError):
+    with pytest.raises((sb.SocpError, ValueError)):
         eng.residual_batch(bad, mp, time, Xb, x)
+    assert sb._lib.lib().socp_residual_batch(eng._h, ctypes.byref(bad), 1, mp.ctypes.data, time.ctypes.data, Xb.ctypes.data,
+                                             x.ctypes.data, x.ctypes.data, 0) != 0          # the C ABI itself refuses it
     bad = shape_of(spec)
     bad.integrator = 1                                                            # dopri5 without a tolerance
     with pytest.raises(sb.SocpError):
