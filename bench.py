@@ -31,9 +31,9 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 FLOPS_PER_RK4_STEP = {"goddard": 1100.0}     # SURVEY.md 8(d) / BASELINE.md section 3 (nominal count)
 # DRAM traffic of hybrd_res_kernel per Broyden iteration of one problem, from the `ncu --set full` capture
-# profiles/r1_final_ncu_res_raw.csv: (dram__bytes_read.sum + dram__bytes_write.sum) = 688.1 MB for the 3678
-# iterations of the captured launch (1.03x the algorithmic 182 KB: no wasted re-reads)
-NCU_DRAM_BYTES_PER_ITERATION = 688.148e6 / 3678
+# profiles/r1_final_ncu_res_raw.csv: (dram__bytes_read.sum + dram__bytes_write.sum) = 663.6 MB for the 3592
+# iterations of the captured launch (1.02x the algorithmic 182 KB: no wasted re-reads)
+NCU_DRAM_BYTES_PER_ITERATION = 663.6e6 / 3592
 METRIC = "shooting solves/sec (Goddard free-tf, M=6, P=85; RK4 steps/sec and % of FP64 roofline alongside)"
 
 
