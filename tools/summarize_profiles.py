@@ -28,9 +28,9 @@ g = lambda n: float(vals[hdr.index(n)].replace(",", ""))
 src = gzip.open(O + "/ncu_res_source.csv.gz", "rt").read().splitlines()
 s2 = next(i for i, l in enumerate(src) if l.startswith('"Address"'))
 its = max(int(x["Instructions Executed"]) for x in csv.DictReader(io.StringIO("\n".join(src[s2:]))) if "REDG.E.ADD.64" in x["Source"])
-out.append("# hybrd_res_kernel capture (--set full): duration %.1f " + units[hdr.index("gpu__time_duration.sum")] + ", dram read %.1f + write %.1f MB, %d Broyden iterations in the launch"
-           " -> %.1f KB of DRAM traffic per iteration (algorithmic 182.0 KB)" % (g("gpu__time_duration.sum"), g("dram__bytes_read.sum"),
-           g("dram__bytes_write.sum"), its, (g("dram__bytes_read.sum") + g("dram__bytes_write.sum")) * 1e3 / its))
+out.append("# hybrd_res_kernel capture (--set full): duration %.1f %s, dram read %.1f + write %.1f MB, %d Broyden iterations in the launch"
+           " -> %.1f KB of DRAM traffic per iteration (algorithmic 182.0 KB)" % (g("gpu__time_duration.sum"), units[hdr.index("gpu__time_duration.sum")],
+           g("dram__bytes_read.sum"), g("dram__bytes_write.sum"), its, (g("dram__bytes_read.sum") + g("dram__bytes_write.sum")) * 1e3 / its))
 out.append("# bench: %.0f solves/s (e2e %.0f), reference arm %.1f solves/s on %d host cores, RK4 kernel %.1f%% of the measured FP64 peak, dominant kernel %s at %.1f%% of %s" % (
     d["value"], d["e2e"]["value"], r["value"], r["cpu_baseline"]["cores"], 100 * d["rk4_kernel"]["frac"], d["roofline"]["kernel"],
     100 * d["roofline"]["frac"], d["roofline"]["bound"]))
