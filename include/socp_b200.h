@@ -106,8 +106,10 @@ int socp_model_default_steps(int model_id);
 int socp_model_default_params(int model_id, double *out);     /* constructor defaults */
 int socp_num_param(const socp_shape *shape);                   /* shooting.cpp:179,196 */
 
-/* obstacle table of the vtolUAV penalty map (src/maps/obstacle/obstacle.cpp:24-36), shared by
- * the whole context; type 0 ellipsoid, 1 box; pos/rad are [n][3].  Host pointers. */
+/* obstacle table of the vtolUAV penalty map (src/maps/obstacle/obstacle.cpp:24-36): type 0 ellipsoid,
+ * 1 box; pos/rad are [n][3], host pointers.  The table lives in constant memory of the DEVICE: it is
+ * shared by every context of the process on that device (empty until first set; creating another
+ * context does not reset it), and setting it waits for the calling context's stream only. */
 int socp_set_obstacles(socp_ctx *ctx, int n, const double *type, const double *pos, const double *rad);
 
 /* ---- hot path ------------------------------------------------------------------------------ */

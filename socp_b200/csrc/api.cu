@@ -198,8 +198,6 @@ int socp_create(int device, socp_ctx **out) {
     cudaMemset(ctx->d_counters, 0, 64 * sizeof(unsigned long long));
     cudaEventCreate(&ctx->ev0);
     cudaEventCreate(&ctx->ev1);
-    int zero = 0;
-    cudaMemcpyToSymbol(c_num_obstacles, &zero, sizeof(int));
     *out = ctx;
     return SOCP_OK;
 }

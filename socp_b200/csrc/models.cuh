@@ -202,14 +202,18 @@ template <> struct Model<DOUBLE_INTEGRATOR> {
 template <> struct Model<COVID19> {
     static constexpr int DIM = 4, N = 8, NP = 8, NCTRL = 1, DEFAULT_STEPS = 1000;
     static constexpr int MINB = 1;
-    struct Ctx { double R0, Tinf, Tinc, Npop, Imax, muI, umin, umax; };
+    // The reference divides by Tinf, Tinc and N thirteen times per RHS; an fp64 divide is ~20 pipe
+    // instructions (123 cycles of latency), so the three reciprocals are formed once per trajectory and the
+    // RHS multiplies (<= 1 ulp per operation, far inside the 1e-12 trajectory tolerance).
+    struct Ctx { double R0, Tinf, Tinc, Npop, Imax, muI, umin, umax, iTinf, iTinc, iN; };
     SOCP_DEV static void load(Ctx &c, const double *m, const double *) {
         c.R0 = m[0]; c.Tinf = m[1]; c.Tinc = m[2]; c.Npop = m[3]; c.Imax = m[4]; c.muI = m[5];
         c.umin = m[6]; c.umax = m[7];
+        c.iTinf = 1.0 / c.Tinf; c.iTinc = 1.0 / c.Tinc; c.iN = 1.0 / c.Npop;
     }
     // covid19.cpp:98-129
     SOCP_DEV static void control(const Ctx &c, double, const double *X, double *u) {
-        double v = (X[5] - X[4]) * X[0] * X[2] / c.Tinf / c.Npop * c.R0;
+        double v = (X[5] - X[4]) * X[0] * X[2] * c.iTinf * c.iN * c.R0;
         if (v <= c.umin) v = c.umin;
         if (v >= c.umax) v = c.umax;
         u[0] = v;
@@ -222,14 +226,15 @@ template <> struct Model<COVID19> {
         double Rt = c.R0 * (1 - u);
         double Ipen = 0;
         if (I >= c.Imax) Ipen = -c.muI * (I - c.Imax);
-        double inf = Rt / c.Tinf / c.Npop * S * I;
+        double inf = Rt * c.iTinf * c.iN * S * I;
+        double EoT = E * c.iTinc, IoT = I * c.iTinf;
         dX[0] = -inf;
-        dX[1] = inf - E / c.Tinc;
-        dX[2] = E / c.Tinc - I / c.Tinf;
-        dX[3] = I / c.Tinf;
-        dX[4] = (pS - pE) * R * I / c.Tinf / c.Npop;
-        dX[5] = (pE - pI) / c.Tinc;
-        dX[6] = (pS - pE) * R * S / c.Tinf / c.Npop + (pI - pR) / c.Tinf + Ipen;
+        dX[1] = inf - EoT;
+        dX[2] = EoT - IoT;
+        dX[3] = IoT;
+        dX[4] = (pS - pE) * R * I * c.iTinf * c.iN;
+        dX[5] = (pE - pI) * c.iTinc;
+        dX[6] = (pS - pE) * R * S * c.iTinf * c.iN + (pI - pR) * c.iTinf + Ipen;
         dX[7] = 0;
     }
     // covid19.cpp:132-168
