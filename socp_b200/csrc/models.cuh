@@ -256,6 +256,7 @@ template <> struct Model<COVID19> {
 // :183-231 (penalty) and :236-316 (gradient; the ellipsoid gradient ignores z, :260-265).
 SOCP_DEV void obstacle_eval(double muObs, double phiObs, const double *pos, double *func, double *grad) {
     double f = 0, g0 = 0, g1 = 0, g2 = 0;
+    const double imu = 1.0 / muObs;
     const int n = c_num_obstacles;
     for (int i = 0; i < n; ++i) {
         const double *o = &c_obstacles[i * 7];
@@ -276,16 +277,22 @@ SOCP_DEV void obstacle_eval(double muObs, double phiObs, const double *pos, doub
                 g1 = g1 - hy / d * (1 + hx * hx * rho2) / muObs * (1 - th * th) / 2;
             }
         } else if (type == 1) {
+            // box: the nine divides per obstacle of the reference (three "/ muObs" in the tanh arguments and
+            // "d / |d| / muObs" in each gradient component) become multiplications by 1/muObs and a sign;
+            // d == 0 keeps the reference's 0/0 = NaN (which zeroes the whole component below)
             double dx = pos[0] - x, dy = pos[1] - y, dz = pos[2] - z;
-            double tx = tanh((fabs(dx) - radx) / muObs);
-            double ty = tanh((fabs(dy) - rady) / muObs);
-            double tz = tanh((fabs(dz) - radz) / muObs);
+            double tx = tanh((fabs(dx) - radx) * imu);
+            double ty = tanh((fabs(dy) - rady) * imu);
+            double tz = tanh((fabs(dz) - radz) * imu);
             double ax = 1 - tx, ay = 1 - ty, az = 1 - tz;
             f = f + ax * ay * az / 8;
             if (grad) {
-                g0 = g0 - dx / fabs(dx) / muObs * (1 - tx * tx) * ay * az / 8;
-                g1 = g1 - dy / fabs(dy) / muObs * (1 - ty * ty) * ax * az / 8;
-                g2 = g2 - dz / fabs(dz) / muObs * (1 - tz * tz) * ax * ay / 8;
+                const double nan_ = __longlong_as_double(0x7ff8000000000000LL);
+                double sx = (dx == 0.) ? nan_ : copysign(imu, dx), sy = (dy == 0.) ? nan_ : copysign(imu, dy),
+                       sz = (dz == 0.) ? nan_ : copysign(imu, dz);
+                g0 = g0 - sx * (1 - tx * tx) * ay * az / 8;
+                g1 = g1 - sy * (1 - ty * ty) * ax * az / 8;
+                g2 = g2 - sz * (1 - tz * tz) * ax * ay / 8;
             }
         }
     }
@@ -326,9 +333,10 @@ template <> struct Model<VTOL_UAV> {
         dX[4] = c.amax * u[1] - c.ca * vy * normV;
         dX[5] = c.amax * u[2] - c.ca * vz * normV;
         dX[6] = 0 - grad[0]; dX[7] = 0 - grad[1]; dX[8] = 0 - grad[2];
-        dX[9] = -p_x + c.ca * (p_vx * (normV + vx * vx / normV) + p_vy * (vy * vx / normV) + p_vz * (vz * vx / normV)) - c.alphaV * vx / normV * (normV - c.Vd);
-        dX[10] = -p_y + c.ca * (p_vy * (normV + vy * vy / normV) + p_vx * (vx * vy / normV) + p_vz * (vz * vy / normV)) - c.alphaV * vy / normV * (normV - c.Vd);
-        dX[11] = -p_z + c.ca * (p_vz * (normV + vz * vz / normV) + p_vx * (vx * vz / normV) + p_vy * (vy * vz / normV)) - c.alphaV * vz / normV * (normV - c.Vd);
+        const double iv = 1.0 / normV;                 // one divide instead of twelve
+        dX[9] = -p_x + c.ca * (p_vx * (normV + vx * vx * iv) + p_vy * (vy * vx * iv) + p_vz * (vz * vx * iv)) - c.alphaV * vx * iv * (normV - c.Vd);
+        dX[10] = -p_y + c.ca * (p_vy * (normV + vy * vy * iv) + p_vx * (vx * vy * iv) + p_vz * (vz * vy * iv)) - c.alphaV * vy * iv * (normV - c.Vd);
+        dX[11] = -p_z + c.ca * (p_vz * (normV + vz * vz * iv) + p_vx * (vx * vz * iv) + p_vy * (vy * vz * iv)) - c.alphaV * vz * iv * (normV - c.Vd);
     }
     // vtolUAV.cpp:151-192
     SOCP_DEV static double hamiltonian(const Ctx &c, double t, const double *X) {
