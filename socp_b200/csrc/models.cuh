@@ -169,14 +169,15 @@ template <> struct Model<GODDARD> {
 template <> struct Model<DOUBLE_INTEGRATOR> {
     static constexpr int DIM = 6, N = 12, NP = 3, NCTRL = 3, DEFAULT_STEPS = 30;
     static constexpr int MINB = 1;
-    struct Ctx { double umax, amax, muT; };
-    SOCP_DEV static void load(Ctx &c, const double *m, const double *) { c.umax = m[0]; c.amax = m[1]; c.muT = m[2]; }
-    // doubleIntegrator.cpp:218-259
+    struct Ctx { double umax, amax, muT, iamax; };
+    SOCP_DEV static void load(Ctx &c, const double *m, const double *) { c.umax = m[0]; c.amax = m[1]; c.muT = m[2]; c.iamax = 1.0 / c.amax; }
+    // doubleIntegrator.cpp:218-259 (u = -p_v / a_max through the hoisted reciprocal; one rsqrt when saturated)
     SOCP_DEV static void control(const Ctx &c, double, const double *X, double *u) {
-        u[0] = -X[9] / c.amax; u[1] = -X[10] / c.amax; u[2] = -X[11] / c.amax;
-        double nu = sqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
-        if (nu > c.umax) {
-            u[0] = u[0] / nu * c.umax; u[1] = u[1] / nu * c.umax; u[2] = u[2] / nu * c.umax;
+        u[0] = -X[9] * c.iamax; u[1] = -X[10] * c.iamax; u[2] = -X[11] * c.iamax;
+        double nu2 = u[0] * u[0] + u[1] * u[1] + u[2] * u[2];
+        if (nu2 > c.umax * c.umax) {
+            double k = c.umax * rsqrt(nu2);
+            u[0] = u[0] * k; u[1] = u[1] * k; u[2] = u[2] * k;
         }
     }
     // doubleIntegrator.cpp:67-108
@@ -415,43 +416,48 @@ template <> struct Model<INTERCEPTOR> {
         double mass = k.mass, c_max = k.c_max, d = k.d, r = k.r, g = k.g, ft = k.ft, eta = c.eta, hr = c.hr;
         double sL, cL;
         sincos(X[4], &sL, &cL);
-        double tL = sL / cL;
+        // one reciprocal per denominator (r, v, mass, cos(L), hr, cos(gamma) / cos(theta)) instead of the ~45
+        // divides per RHS of the formulas as written
+        const double ir = 1.0 / r, iv = 1.0 / v, im = 1.0 / mass, icL = 1.0 / cL, ihr = 1.0 / hr;
+        double tL = sL * icL;
         double u, beta, sb, cb;
         if (c.chart == 1) {
             double p_gamma = X[8], p_chi = X[9];
             double sg, cg, sc, cc;
             sincos(X[2], &sg, &cg);
             sincos(X[3], &sc, &cc);
+            const double icg = 1.0 / cg;
             control_full(c, k, X, cg, u, beta, sb, cb);
             double sa, ca;
             sincos(c.alphamax * u, &sa, &ca);
             double dd = d + eta * c_max * u * u;
             dX[0] = v * sg;
-            dX[1] = -dd * v * v - g * sg + ft * ca / mass;
-            dX[2] = v * c_max * u * cb - g / v * cg + ft * sa * cb / mass / v + v * cg / r;
-            dX[3] = v * c_max * u * sb / cg + ft * sa * sb / cg / mass / v + v * cg * tL * sc / r;
-            dX[4] = v * cg * cc / r;
-            dX[5] = v * cg * sc / cL / r;
-            dX[6] = -p_v / hr * dd * v * v - 2 * g / r * (p_gamma / v * cg + p_v * sg)
-                  + p_L * v * cg * cc / r / r + p_gamma * v * cg / r / r + p_gamma * v * c_max * u * cb / hr
-                  + p_l * v * cg * sc / cL / r / r + p_chi * v * cg * tL * sc / r / r + p_chi * v * c_max * u * sb / cg / hr;
-            dX[7] = -(p_L * cg * cc / r + p_l * cg * sc / cL / r + p_h * sg
-                      + p_gamma * (c_max * u * cb + g / v / v * cg - ft * sa * cb / mass / v / v + cg / r)
-                      + p_chi * (c_max * u * sb / cg - ft * sa * sb / cg / mass / v / v + cg * tL * sc / r)
+            dX[1] = -dd * v * v - g * sg + ft * ca * im;
+            dX[2] = v * c_max * u * cb - g * iv * cg + ft * sa * cb * im * iv + v * cg * ir;
+            dX[3] = v * c_max * u * sb * icg + ft * sa * sb * icg * im * iv + v * cg * tL * sc * ir;
+            dX[4] = v * cg * cc * ir;
+            dX[5] = v * cg * sc * icL * ir;
+            dX[6] = -p_v * ihr * dd * v * v - 2 * g * ir * (p_gamma * iv * cg + p_v * sg)
+                  + p_L * v * cg * cc * ir * ir + p_gamma * v * cg * ir * ir + p_gamma * v * c_max * u * cb * ihr
+                  + p_l * v * cg * sc * icL * ir * ir + p_chi * v * cg * tL * sc * ir * ir + p_chi * v * c_max * u * sb * icg * ihr;
+            dX[7] = -(p_L * cg * cc * ir + p_l * cg * sc * icL * ir + p_h * sg
+                      + p_gamma * (c_max * u * cb + g * iv * iv * cg - ft * sa * cb * im * iv * iv + cg * ir)
+                      + p_chi * (c_max * u * sb * icg - ft * sa * sb * icg * im * iv * iv + cg * tL * sc * ir)
                       - p_v * 2 * dd * v);
-            dX[8] = v * (p_L * sg * cc / r + p_l * sg * sc / cL / r - p_h * cg)
-                  - g * (p_gamma / v * sg - p_v * cg)
-                  + p_gamma * v * sg / r + p_chi * v * sg * tL * sc / r
-                  - p_chi * (v * c_max * u * sb + ft * sa * sb / mass / v) * sg / cg / cg;
-            dX[9] = v * (p_L * cg * sc / r - p_l * cg * cc / cL / r - p_chi * cg * tL * cc / r);
-            dX[10] = -p_l * v * cg * sc * sL / cL / cL / r - p_chi * v * cg * (1 + tL * tL) * sc / r;
+            dX[8] = v * (p_L * sg * cc * ir + p_l * sg * sc * icL * ir - p_h * cg)
+                  - g * (p_gamma * iv * sg - p_v * cg)
+                  + p_gamma * v * sg * ir + p_chi * v * sg * tL * sc * ir
+                  - p_chi * (v * c_max * u * sb + ft * sa * sb * im * iv) * sg * icg * icg;
+            dX[9] = v * (p_L * cg * sc * ir - p_l * cg * cc * icL * ir - p_chi * cg * tL * cc * ir);
+            dX[10] = -p_l * v * cg * sc * sL * icL * icL * ir - p_chi * v * cg * (1 + tL * tL) * sc * ir;
             dX[11] = 0.0;
         } else {
             double p_theta = X[8], p_phi = X[9];
             double st, ct, sp, cp;
             sincos(X[2], &st, &ct);
             sincos(X[3], &sp, &cp);
-            double tt = st / ct;
+            const double ict = 1.0 / ct;
+            double tt = st * ict;
             control_full(c, k, X, ct, u, beta, sb, cb);
             double sa, ca;
             sincos(c.alphamax * u, &sa, &ca);
@@ -459,28 +465,28 @@ template <> struct Model<INTERCEPTOR> {
             double w1 = cp + sp * tL;                       // cos(phi) + sin(phi) tan(L)
             double w2 = sp + tt * tt * (sp - tL * cp);      // sin(phi) + tan^2(theta)(sin(phi) - tan(L) cos(phi))
             dX[0] = -v * ct * cp;
-            dX[1] = -dd * v * v + g * ct * cp + ft * ca / mass;
-            dX[2] = v * c_max * u * cb + v * st * w1 / r + (ft * sa * cb / (mass * v) - g * st * cp / v);
-            dX[3] = -v * c_max * u * sb / ct + v * ct * w2 / r - (ft * sa * sb / (mass * v * ct) + g * sp / (v * ct));
-            dX[4] = v * ct * sp / r;
-            dX[5] = v * st / (r * cL);
-            dX[6] = -p_v / hr * dd * v * v - 2 * g / r * (p_theta * st * cp / v + p_phi * sp / ct / v - p_v * ct * cp)
-                  + p_L * v * ct * sp / r / r + v * p_theta * st * w1 / r / r + p_theta * v * c_max * u * cb / hr
-                  + p_l * v * st / cL / r / r + v * p_phi * ct * w2 / r / r - p_phi * v * c_max * u * sb / ct / hr;
-            dX[7] = -(p_L * ct * sp / r + p_l * st / (r * cL) - p_h * ct * cp
-                      + p_theta * (c_max * u * cb + g / v / v * st * cp - ft * sa * cb / mass / v / v + st * w1 / r)
-                      + p_phi * (-c_max * u * sb / ct + g / v / v * sp / ct + ft * sa * sb / ct / mass / v / v + ct * w2 / r)
+            dX[1] = -dd * v * v + g * ct * cp + ft * ca * im;
+            dX[2] = v * c_max * u * cb + v * st * w1 * ir + (ft * sa * cb * (im * iv) - g * st * cp * iv);
+            dX[3] = -v * c_max * u * sb * ict + v * ct * w2 * ir - (ft * sa * sb * (im * iv * ict) + g * sp * (iv * ict));
+            dX[4] = v * ct * sp * ir;
+            dX[5] = v * st * (ir * icL);
+            dX[6] = -p_v * ihr * dd * v * v - 2 * g * ir * (p_theta * st * cp * iv + p_phi * sp * ict * iv - p_v * ct * cp)
+                  + p_L * v * ct * sp * ir * ir + v * p_theta * st * w1 * ir * ir + p_theta * v * c_max * u * cb * ihr
+                  + p_l * v * st * icL * ir * ir + v * p_phi * ct * w2 * ir * ir - p_phi * v * c_max * u * sb * ict * ihr;
+            dX[7] = -(p_L * ct * sp * ir + p_l * st * (ir * icL) - p_h * ct * cp
+                      + p_theta * (c_max * u * cb + g * iv * iv * st * cp - ft * sa * cb * im * iv * iv + st * w1 * ir)
+                      + p_phi * (-c_max * u * sb * ict + g * iv * iv * sp * ict + ft * sa * sb * ict * im * iv * iv + ct * w2 * ir)
                       - p_v * 2 * dd * v);
-            dX[8] = -v * (-p_L * st * sp / r + p_l * ct / (r * cL) + p_h * st * cp)
-                  - g * (-p_theta * ct * cp / v - p_phi * sp * tt / (v * ct) - p_v * st * cp)
-                  - p_theta * v * ct * w1 / r + p_phi * v * st * w2 / r
-                  - p_phi * v * ct * (2 * tt * (1 + tt * tt) * (sp - tL * cp)) / r
-                  - p_phi * (-v * c_max * u * sb - ft * sa * sb / mass / v) * tt / ct;
-            dX[9] = -v * (p_h * ct * sp + p_L * ct * cp / r)
-                  - g * (p_theta * st * sp / v - p_phi * cp / (v * ct) - p_v * ct * sp)
-                  - p_theta * (v * st * (-sp + cp * tL) / r)
-                  - p_phi * v * ct * (cp + tt * tt * (cp + tL * sp)) / r;
-            dX[10] = -p_l * v * st * tL / cL / r - v * (1 + tL * tL) * (p_theta * st * sp - p_phi * ct * cp * tt * tt) / r;
+            dX[8] = -v * (-p_L * st * sp * ir + p_l * ct * (ir * icL) + p_h * st * cp)
+                  - g * (-p_theta * ct * cp * iv - p_phi * sp * tt * (iv * ict) - p_v * st * cp)
+                  - p_theta * v * ct * w1 * ir + p_phi * v * st * w2 * ir
+                  - p_phi * v * ct * (2 * tt * (1 + tt * tt) * (sp - tL * cp)) * ir
+                  - p_phi * (-v * c_max * u * sb - ft * sa * sb * im * iv) * tt * ict;
+            dX[9] = -v * (p_h * ct * sp + p_L * ct * cp * ir)
+                  - g * (p_theta * st * sp * iv - p_phi * cp * (iv * ict) - p_v * ct * sp)
+                  - p_theta * (v * st * (-sp + cp * tL) * ir)
+                  - p_phi * v * ct * (cp + tt * tt * (cp + tL * sp)) * ir;
+            dX[10] = -p_l * v * st * tL * icL * ir - v * (1 + tL * tL) * (p_theta * st * sp - p_phi * ct * cp * tt * tt) * ir;
             dX[11] = 0.0;
         }
     }
