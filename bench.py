@@ -287,8 +287,8 @@ def main():
     sampler.join(timeout=2)
 
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    agg = torch.tensor([st["rk4_steps"], float((d_info == 1).sum().item()), float(d_nfev.sum().item())],
-                       dtype=torch.float64, device=dev)
+    agg = torch.tensor([st["rk4_steps"], float((d_info == 1).sum().item()), float(d_nfev.sum().item()),
+                        float(((d_info == 1) & (d_fnorm < 1e-5)).sum().item())], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(agg, op=dist.ReduceOp.SUM)
@@ -419,7 +419,8 @@ def main():
                        "parallelism": "problems sharded, %d rank(s), no data-path collective; results all-gathered" % world,
                        "l2": "working set %.1f GB per GPU >> 126 MB L2, no flush needed" % (st["device_bytes"] / 1e9)},
             "rk4_steps_per_s": rk4_rate, "rk4_steps_per_step": rk4_steps_per_step,
-            "converged_fraction": float(agg[1].item()) / (world * B),
+            "converged_fraction": float(agg[1].item()) / (world * B),            # info == 1, what SOCP accepts
+            "true_root_fraction": float(agg[3].item()) / (world * B),            # info == 1 and |F| < 1e-5
             "mean_nfev": float(agg[2].item()) / (world * B),
             "solver_rounds_per_step": st["solver_rounds"] / args.steps,
             "gpu_launches": int(st["kernel_launches"]),
