@@ -306,8 +306,15 @@ int run_solver(socp_ctx *ctx, const socp_shape *shape, long B, const double *d_m
         ctx->launches += 1;
         int cur = 0, pending = 0;
         int entering[2] = {(int)Bw, 0};
+        // live problems as of the last look at the counters: they only retire, so this bounds the work of
+        // every later round; the grids follow it (every kernel strides over its work list, so any grid is
+        // correct) and the tail of a solve -- a handful of live problems -- stops launching 1184 idle CTAs
+        long live = Bw;
         for (long round = 0; round < max_rounds; ++round) {
-            launch_round_any(ctx, D, cur, grid_int, grid_adv, ctx->profile ? pending : -1);
+            const long items = live * std::max(D.nJ, D.P);                       // upper bound on work items
+            const int gi = (int)std::max<long>(1, std::min<long>(grid_int, (items + 127) / 128));
+            const int ga = (int)std::max<long>(1, std::min<long>(grid_adv, live));
+            launch_round_any(ctx, D, cur, gi, ga, ctx->profile ? pending : -1);
             ++pending;
             cur = 1 - cur;
             if (run_mode == RUN_SOLVE && (round % check_every) == check_every - 1) {
@@ -317,6 +324,7 @@ int run_solver(socp_ctx *ctx, const socp_shape *shape, long B, const double *d_m
                 if (ctx->profile) prof_harvest(ctx, pending, round_log, round, entering);
                 pending = 0;
                 entering[0] = ctx->solver.h_counts[cur * 2]; entering[1] = ctx->solver.h_counts[cur * 2 + 1];
+                live = (long)entering[0] + entering[1];
                 if (ctx->solver.h_counts[cur * 2] + ctx->solver.h_counts[cur * 2 + 1] == 0) break;
             }
         }
