@@ -21,6 +21,7 @@
 // shooting.cpp:803-826 (ml = mu = n-1, epsfcn = 1e-15, mode = 1, factor = 1).
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda_pipeline.h>
 #include <float.h>
 #include "../../include/socp_b200.h"
 #include "models.cuh"
@@ -693,6 +694,16 @@ template <int G> SOCP_DEV void gcopy(double *dst, const double *src, int n) {
     }
 }
 
+// global -> shared with cp.async (LDGSTS): every element of the copy is in flight at once, no register
+// staging; complete with gcopy_async_wait() + a barrier.  dst must be shared memory.
+template <int G> SOCP_DEV void gcopy_async(double *dst, const double *src, int n) {
+    for (int i = threadIdx.x % G; i < n; i += G) __pipeline_memcpy_async(dst + i, src + i, sizeof(double));
+}
+SOCP_DEV void gcopy_async_wait() {
+    __pipeline_commit();
+    __pipeline_wait_prior(0);
+}
+
 // ask L2 for [p, p + bytes): one prefetch per 128-byte line, spread over the group
 template <int G> SOCP_DEV void l2_prefetch(const void *p, size_t bytes) {
     const char *c = (const char *)p;
@@ -1287,10 +1298,11 @@ hybrd_res_kernel(SolverDev D, int cur, int per_group_doubles) {
         W.q = D.fjac + (size_t)b * n * n;
         W.ldq = n;
         l2_prefetch<G>(W.q, (size_t)n * n * sizeof(double));      // Q is first touched ~20 us from now
-        gcopy<G>(W.x, D.x + b * n, n); gcopy<G>(W.xe, D.xe + b * n, n); gcopy<G>(W.fvec, D.fvec + b * n, n);
-        gcopy<G>(W.diag, D.diag + b * n, n); gcopy<G>(W.qtf, D.qtf + b * n, n); gcopy<G>(W.wa1, D.wa1 + b * n, n);
-        gcopy<G>(W.wa4, D.wa4 + b * n, n);
-        if (STAGE_R) gcopy<G>(W.r, D.r + (size_t)b * D.LR, D.LR);
+        gcopy_async<G>(W.x, D.x + b * n, n); gcopy_async<G>(W.xe, D.xe + b * n, n); gcopy_async<G>(W.fvec, D.fvec + b * n, n);
+        gcopy_async<G>(W.diag, D.diag + b * n, n); gcopy_async<G>(W.qtf, D.qtf + b * n, n); gcopy_async<G>(W.wa1, D.wa1 + b * n, n);
+        gcopy_async<G>(W.wa4, D.wa4 + b * n, n);
+        if (STAGE_R) gcopy_async<G>(W.r, D.r + (size_t)b * D.LR, D.LR);
+        gcopy_async_wait();
         gsync<G>();
         SOCP_PHASE(16, 0);
 
@@ -1464,10 +1476,11 @@ hybrd_jac_kernel(SolverDev D, int cur, int per_group_doubles) {
         W.q = STAGE_Q ? after : gq;
         W.ldq = STAGE_Q ? ldq_s : n;
         long long phase_t0 = clock64();
-        gcopy<G>(W.x, D.x + b * n, n); gcopy<G>(W.fvec, D.fvec + b * n, n); gcopy<G>(W.diag, D.diag + b * n, n);
+        gcopy_async<G>(W.x, D.x + b * n, n); gcopy_async<G>(W.fvec, D.fvec + b * n, n); gcopy_async<G>(W.diag, D.diag + b * n, n);
         if (STAGE_Q)
             for (int c = tid >> 5; c < n; c += G / 32)
-                for (int i = tid & 31; i < n; i += 32) W.q[i + (size_t)c * ldq_s] = gq[i + (size_t)c * n];
+                for (int i = tid & 31; i < n; i += 32) __pipeline_memcpy_async(W.q + i + (size_t)c * ldq_s, gq + i + (size_t)c * n, sizeof(double));
+        gcopy_async_wait();
         gsync<G>();
         SOCP_PHASE(32, 0);
         if (tid == 0) {
