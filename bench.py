@@ -241,7 +241,7 @@ def main():
     eng = sb.Engine(local)
     peak_gflops, clk = eng.measure_fp64_peak()
     B = args.batch
-    shape, mp, time_, Xb, x0 = goddard_workload(eng, B, seed=20260002 + rank)
+    shape, mp, time_, Xb, x0 = goddard_workload(eng, B, seed=20260002 + rank + int(os.environ.get("SOCP_BENCH_SEED_OFFSET", "0")))
     P = x0.shape[1]
 
     def dv(a):

@@ -10,5 +10,6 @@ PY
 for v in "$@"; do
   case $v in
     base) run base X=1;;
+    seed*) run $v SOCP_BENCH_SEED_OFFSET=${v#seed};;
   esac
 done
