@@ -31,9 +31,9 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 FLOPS_PER_RK4_STEP = {"goddard": 1100.0}     # SURVEY.md 8(d) / BASELINE.md section 3 (nominal count)
 # DRAM traffic of hybrd_res_kernel per Broyden iteration of one problem, from the `ncu --set full` capture
-# profiles/r1_final_ncu_res_raw.csv: (dram__bytes_read.sum + dram__bytes_write.sum) = 663.6 MB for the 3592
+# profiles/r1_final_ncu_res_raw.csv: (dram__bytes_read.sum + dram__bytes_write.sum) = 664.3 MB for the 3592
 # iterations of the captured launch (1.02x the algorithmic 182 KB: no wasted re-reads)
-NCU_DRAM_BYTES_PER_ITERATION = 663.6e6 / 3592
+NCU_DRAM_BYTES_PER_ITERATION = 664.3e6 / 3592
 METRIC = "shooting solves/sec (Goddard free-tf, M=6, P=85; RK4 steps/sec and % of FP64 roofline alongside)"
 
 
@@ -222,6 +222,12 @@ def main():
         run_reference(args, rank)
         return
 
+    # stdout carries exactly ONE JSON line: anything libraries print there (NCCL's version banner, ...) goes
+    # to stderr instead
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
     import socp_b200 as sb
@@ -286,6 +292,9 @@ def main():
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
+    if world > 1:
+        print("rank %d: %.1f ms for %d step(s), %d solver rounds, res %.0f jac %.0f ms" %
+              (rank, ms, args.steps, st["solver_rounds"], st["advance_ms"] - st["jac_ms"], st["jac_ms"]), file=sys.stderr)
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     agg = torch.tensor([st["rk4_steps"], float((d_info == 1).sum().item()), float(d_nfev.sum().item()),
                         float(((d_info == 1) & (d_fnorm < 1e-5)).sum().item())], dtype=torch.float64, device=dev)
@@ -427,7 +436,7 @@ def main():
             "roofline": roofline, "rk4_kernel": rk4_kernel, "e2e": e2e, "cpu_baseline": cpu_baseline,
             "clocks": sampler.summary(), "fp64_peak_probe_sm_mhz": clk,
         }
-        print(json.dumps(line))
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
