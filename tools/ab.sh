@@ -10,6 +10,7 @@ PY
 for v in "$@"; do
   case $v in
     base) run base X=1;;
+    clocks) run clocks SOCP_PHASE_CLOCKS=1; grep -h 'phase clocks' $O/clocks.err | tail -1;;
     seed*) run $v SOCP_BENCH_SEED_OFFSET=${v#seed};;
   esac
 done
