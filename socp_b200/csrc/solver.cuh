@@ -827,18 +827,15 @@ __device__ void qform_g(int n, double *q, int lda, double *wa, int rot, const in
     }
 }
 
-// y[i] = add[i] + sum_{j >= i} R(i,j) v[j]   (one warp per row, lanes along the packed row)
+// y[i] = add[i] + sum_{j >= i} R(i,j) v[j]   (one thread per packed row, four running sums: a row per
+// warp with a shuffle reduction per row cost 10x the instructions -- 85 reductions per call, two calls
+// per Broyden iteration -- and was the top line of the kernel's profile)
 template <int G>
 __device__ void rmulv_g(int n, const double *r, const double *v, const double *add, double *y) {
-    const int lane = threadIdx.x & 31, warp = (threadIdx.x % G) >> 5;
+    const int tid = threadIdx.x % G;
     gsync<G>();
-    for (int i = warp; i < n; i += G / 32) {
-        const double *ri = r + rowstart(n, i);
-        double part = 0.;
-        for (int j = i + lane; j < n; j += 32) part += ri[j - i] * v[j];
-        const double s = warp_sum(part);
-        if (lane == 0) y[i] = (add ? add[i] : 0.) + s;
-    }
+    for (int i = tid; i < n; i += G)
+        y[i] = (add ? add[i] : 0.) + dot4(r + rowstart(n, i), v + i, n - i);
     gsync<G>();
 }
 
@@ -916,7 +913,8 @@ __device__ void dogleg_g(int n, const double *r, const double *diag, const doubl
     // scaled gradient direction: wa1 = (R^T qtb) / diag   (one thread per column)
     for (int i = tid; i < n; i += G) {
         double s = 0.;
-        for (int j = 0; j <= i; ++j) s += r[rowstart(n, j) + (i - j)] * qtb[j];
+        int l = i;                                             // R(j, i) in the packed rows
+        for (int j = 0; j <= i; ++j) { s += r[l] * qtb[j]; l += n - 1 - j; }
         wa1[i] = s / diag[i];
     }
     gsync<G>();
