@@ -967,6 +967,49 @@ SOCP_DEV double givens_tau(double a, double b, double c, double sgl) {
     return sgl;
 }
 
+// steps j = 32 PH .. j_end - 1 of the second sweep of r1updt for n <= 96 (see r1updt_g): w in registers, three
+// slots per lane (i = lane, lane + 32, lane + 64)
+template <int PH>
+SOCP_DEV void sweep2_phase(int n, double *s, double *cs, double *sn, double *tmp, int lane, int j_end,
+                           double &w0, double &w1, double &w2, double &wj, double &sjj, int &jj) {
+    const unsigned FULL = 0xffffffffu;
+    const int i0 = lane, i1 = lane + 32, i2 = lane + 64;
+    const bool in1 = i1 < n, in2 = i2 < n;
+    for (int j = 32 * PH; j < j_end; ++j) {
+        const bool a0 = PH == 0 && i0 > j && i0 < n;
+        const bool a1 = PH == 0 ? in1 : (PH == 1 && i1 > j && in1);
+        const bool a2 = PH <= 1 ? in2 : (i2 > j && in2);
+        const int base = jj - j;
+        double s0 = 0., s1 = 0., s2 = 0.;
+        if (PH == 0) s0 = a0 ? s[base + i0] : 0.;
+        if (PH <= 1) s1 = a1 ? s[base + i1] : 0.;
+        s2 = a2 ? s[base + i2] : 0.;
+        const int jjn = jj + (n - j);
+        const double sjj_next = s[jjn];
+        double c = 1., sgl = 0.;
+        const bool rot = wj != 0.;                         // uniform
+        if (rot) givens(sjj, wj, c, sgl);
+        if (rot) {
+            if (PH == 0 && a0) s[base + i0] = fma(c, s0, sgl * w0);
+            if (PH <= 1 && a1) s[base + i1] = fma(c, s1, sgl * w1);
+            if (a2) s[base + i2] = fma(c, s2, sgl * w2);
+            if (PH == 0 && a0) w0 = fma(c, w0, -sgl * s0);
+            if (PH <= 1 && a1) w1 = fma(c, w1, -sgl * s1);
+            if (a2) w2 = fma(c, w2, -sgl * s2);
+        }
+        if (lane == (j & 31)) {
+            if (rot) { s[jj] = fma(c, sjj, sgl * wj); cs[j] = c; sn[j] = sgl; }
+            tmp[j] = rot ? ((fabs(sjj) < fabs(wj)) ? 1. : 0.) : 2.;
+        }
+        // the next pivot w[j + 1] sits in slot PH, or in the next slot at the end of the phase
+        const bool wrap = ((j + 1) & 31) == 0;
+        const double pick = (PH == 0) ? (wrap ? w1 : w0) : (PH == 1) ? (wrap ? w2 : w1) : w2;
+        wj = __shfl_sync(FULL, pick, (j + 1) & 31);
+        sjj = sjj_next;
+        jj = jjn;
+    }
+}
+
 // r1updt on the packed upper-triangular factor (m == n): (R + u v^T) -> R' with the 2(n-1) Givens
 // rotations recorded in v and w for r1mpyq.  cs/sn are scratch [n] each, tmp is scratch [2n].
 template <int G>
@@ -1051,10 +1094,11 @@ __device__ void r1updt_g(int n, double *s, const double *u, double *v, double *w
     // apply to the columns: column i is touched by rotations j = min(i, n-2) .. 0
     for (int i = tid; i < n; i += G) {
         double wi = (i == n - 1) ? s[rowstart(n, n - 1)] : 0.;
-        for (int j = (i < n - 1 ? i : n - 2); j >= 0; --j) {
+        const int jtop = (i < n - 1 ? i : n - 2);
+        int l = rowstart(n, jtop) + (i - jtop);                // S(j, i) in the packed rows, one row up per step
+        for (int j = jtop; j >= 0; l -= n - j, --j) {
             const double c = cs[j];
             if (c > 1.5) continue;
-            const int l = rowstart(n, j) + (i - j);
             const double sl = s[l];
             s[l] = c * sl - sn[j] * wi;
             wi = sn[j] * sl + c * wi;
@@ -1075,33 +1119,11 @@ __device__ void r1updt_g(int n, double *s, const double *u, double *v, double *w
             double wj = __shfl_sync(FULL, w0, 0);
             double sjj = s[0];
             int jj = 0;                                            // rowstart(n, j)
-            for (int j = 0; j < n - 1; ++j) {
-                const int i0 = lane, i1 = lane + 32, i2 = lane + 64;
-                const bool a0 = i0 > j && i0 < n, a1 = i1 > j && i1 < n, a2 = i2 > j && i2 < n;
-                const double s0 = a0 ? s[jj + (i0 - j)] : 0., s1 = a1 ? s[jj + (i1 - j)] : 0., s2 = a2 ? s[jj + (i2 - j)] : 0.;
-                const int jjn = jj + (n - j);
-                const double sjj_next = s[jjn];
-                double c = 1., sgl = 0.;
-                const bool rot = wj != 0.;                         // uniform
-                if (rot) givens(sjj, wj, c, sgl);
-                if (rot) {
-                    if (a0) s[jj + (i0 - j)] = fma(c, s0, sgl * w0);
-                    if (a1) s[jj + (i1 - j)] = fma(c, s1, sgl * w1);
-                    if (a2) s[jj + (i2 - j)] = fma(c, s2, sgl * w2);
-                    if (a0) w0 = fma(c, w0, -sgl * s0);
-                    if (a1) w1 = fma(c, w1, -sgl * s1);
-                    if (a2) w2 = fma(c, w2, -sgl * s2);
-                }
-                if (lane == (j & 31)) {
-                    if (rot) { s[jj] = fma(c, sjj, sgl * wj); cs[j] = c; sn[j] = sgl; }
-                    tmp[j] = rot ? ((fabs(sjj) < fabs(wj)) ? 1. : 0.) : 2.;
-                }
-                const int slot = (j + 1) >> 5;
-                const double pick = (slot == 0) ? w0 : (slot == 1) ? w1 : w2;
-                wj = __shfl_sync(FULL, pick, (j + 1) & 31);
-                sjj = sjj_next;
-                jj = jjn;
-            }
+            // three phases of 32 steps: in phase p the slots below p are finished (no loads, no FMAs for them)
+            // and the slots above p are active in every step
+            sweep2_phase<0>(n, s, cs, sn, tmp, lane, min(32, n - 1), w0, w1, w2, wj, sjj, jj);
+            sweep2_phase<1>(n, s, cs, sn, tmp, lane, min(64, n - 1), w0, w1, w2, wj, sjj, jj);
+            sweep2_phase<2>(n, s, cs, sn, tmp, lane, n - 1, w0, w1, w2, wj, sjj, jj);
             // w[j] for j < n - 1 is replaced by tau below; only the last entry keeps its value
             if (lane == ((n - 1) & 31)) w[n - 1] = ((n - 1) >> 5) == 0 ? w0 : ((n - 1) >> 5) == 1 ? w1 : w2;
             for (int j = lane; j < n - 1; j += 32) if (tmp[j] == 2.) w[j] = 0.;
@@ -1165,14 +1187,16 @@ __device__ void r1coef_g(int n, const double *v, const double *w, double *scr) {
 
 // r1mpyq: apply the recorded rotations to A (m x n, column-major, lda): one thread per row, the
 // row streamed through registers in chunks of 8 columns so that the loads overlap the chain.
+// `extra` (length n, stride 1) is transformed as one more row (r1mpyq(1, n, qtf, 1, ...) of hybrd).
 template <int G>
-__device__ void r1mpyq_g(int m, int n, double *a, int lda, const double *scr) {
+__device__ void r1mpyq_g(int m, int n, double *a, int lda_a, const double *scr, double *extra) {
     const int tid = threadIdx.x % G;
     const double *c1 = scr, *s1 = scr + n, *c2 = scr + 2 * n, *s2 = scr + 3 * n;
     constexpr int CH = 8;
     gsync<G>();
-    for (int i = tid; i < m; i += G) {
-        double *row = a + i;
+    for (int i = tid; i < m + 1; i += G) {
+        double *row = (i < m) ? a + i : extra;
+        const int lda = (i < m) ? lda_a : 1;
         double an = row[(size_t)(n - 1) * lda];
         double buf[CH];
         for (int j0 = n - 2; j0 >= 0; j0 -= CH) {             // first set: j = n-2 .. 0
@@ -1402,11 +1426,36 @@ hybrd_res_kernel(SolverDev D, int cur, int per_group_doubles) {
                         }
                     }
                     SOCP_SUB(0);
+                    // transposing butterfly: 9 shuffles leave the sum of column j0 + (lane >> 2) in every lane
+                    // (8 separate reductions take 40), then eight lanes finish their columns in parallel
+                    double q4[4], q2[2];
+                    {
+                        const bool up = lane & 16;
 #pragma unroll
-                    for (int k = 0; k < NC; ++k) {
-                        const int j = j0 + k;
-                        const double sum = warp_sum(part[k]);
-                        if (j < n && lane == 0) {
+                        for (int k = 0; k < 4; ++k) {
+                            const double recv = __shfl_xor_sync(0xffffffffu, up ? part[k] : part[k + 4], 16);
+                            q4[k] = (up ? part[k + 4] : part[k]) + recv;
+                        }
+                    }
+                    {
+                        const bool up = lane & 8;
+#pragma unroll
+                        for (int k = 0; k < 2; ++k) {
+                            const double recv = __shfl_xor_sync(0xffffffffu, up ? q4[k] : q4[k + 2], 8);
+                            q2[k] = (up ? q4[k + 2] : q4[k]) + recv;
+                        }
+                    }
+                    double sum;
+                    {
+                        const bool up = lane & 4;
+                        const double recv = __shfl_xor_sync(0xffffffffu, up ? q2[0] : q2[1], 4);
+                        sum = (up ? q2[1] : q2[0]) + recv;
+                    }
+                    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+                    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+                    {
+                        const int j = j0 + (lane >> 2);
+                        if (j < n && (lane & 3) == 0) {
                             W.wa2[j] = (sum - W.wa3[j]) / pnorm;
                             W.wa1[j] = W.diag[j] * ((W.diag[j] * W.wa1[j]) / pnorm);
                             if (ratio >= p0001) W.qtf[j] = sum;
@@ -1421,8 +1470,7 @@ hybrd_res_kernel(SolverDev D, int cur, int per_group_doubles) {
             r1updt_g<G>(n, W.r, W.wa1, W.wa2, W.wa3, W.scr, W.scr + n, W.scr + 2 * n, seq_warp<G>(D.sm_count), D.phase_clocks, D.counters);
             SOCP_PHASE(16, 4);
             r1coef_g<G>(n, W.wa2, W.wa3, W.scr);
-            r1mpyq_g<G>(n, n, W.q, W.ldq, W.scr);
-            r1mpyq_g<G>(1, n, W.qtf, 1, W.scr);
+            r1mpyq_g<G>(n, n, W.q, W.ldq, W.scr, W.qtf);
             SOCP_PHASE(16, 5);
             if (tid == 0) is[I_JEVAL] = 0;
             dogleg_and_request<G>(D, b, W, is, ds, red, next_res, next_cnt);
