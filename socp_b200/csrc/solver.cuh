@@ -839,6 +839,25 @@ __device__ void rmulv_g(int n, const double *r, const double *v, const double *a
     gsync<G>();
 }
 
+// steps j = min(32 PH + 31, n - 1) .. 32 PH of dogleg's back substitution for n <= 96 (see dogleg_g)
+template <int PH>
+SOCP_DEV void backsub_phase(int n, const double *r, const double *dinvs, const double *ds, int lane,
+                            double &b0, double &b1, double &b2, int &p0, int &p1, int &p2) {
+    for (int j = min(32 * PH + 31, n - 1); j >= 32 * PH; --j) {
+        const double bj = (PH == 0) ? b0 : (PH == 1) ? b1 : b2;
+        const double d = ds[j], dinv = dinvs[j];
+        const double q0 = bj * dinv;
+        const double xj = __shfl_sync(0xffffffffu, fma(fma(-q0, d, bj), dinv, q0), j & 31);
+        // rows i < j: every row of the slots below PH, the rows i < j of slot PH
+        const double r0 = (PH > 0 || lane < j) ? r[p0] : 0.;
+        b0 = fma(-r0, xj, b0);
+        if (PH >= 1) { const double r1 = (PH > 1 || lane + 32 < j) ? r[p1] : 0.; b1 = fma(-r1, xj, b1); }
+        if (PH == 2) { const double r2 = (lane + 64 < j) ? r[p2] : 0.; b2 = fma(-r2, xj, b2); }
+        if (lane == (j & 31)) { if (PH == 0) b0 = xj; else if (PH == 1) b1 = xj; else b2 = xj; }
+        --p0; --p1; --p2;
+    }
+}
+
 // dogleg: x <- step; wa1, wa2 scratch
 template <int G>
 __device__ void dogleg_g(int n, const double *r, const double *diag, const double *qtb, double delta,
@@ -874,17 +893,11 @@ __device__ void dogleg_g(int n, const double *r, const double *diag, const doubl
             // p_k: index of R(i_k, j) in the packed rows, moves one to the left per step
             int p0 = rowstart(n, lane) + (n - 1 - lane), p1 = rowstart(n, lane + 32) + (n - 1 - lane - 32),
                 p2 = rowstart(n, lane + 64) + (n - 1 - lane - 64);
-            for (int j = n - 1; j >= 0; --j) {
-                const int slot = j >> 5;
-                const double bj = (slot == 0) ? b0 : (slot == 1) ? b1 : b2;
-                const double d = wa2[j], dinv = wa1[j];
-                const double q0 = bj * dinv;
-                const double xj = __shfl_sync(0xffffffffu, fma(fma(-q0, d, bj), dinv, q0), j & 31);
-                const double r0 = (lane < j) ? r[p0] : 0., r1 = (lane + 32 < j) ? r[p1] : 0., r2 = (lane + 64 < j) ? r[p2] : 0.;
-                b0 = fma(-r0, xj, b0); b1 = fma(-r1, xj, b1); b2 = fma(-r2, xj, b2);
-                if (lane == (j & 31)) { if (slot == 0) b0 = xj; else if (slot == 1) b1 = xj; else b2 = xj; }
-                --p0; --p1; --p2;
-            }
+            // three phases of 32 steps (pivots in slot 2, 1, 0): the slots above the pivot's are finished, the
+            // ones below are active in every step
+            backsub_phase<2>(n, r, wa1, wa2, lane, b0, b1, b2, p0, p1, p2);
+            backsub_phase<1>(n, r, wa1, wa2, lane, b0, b1, b2, p0, p1, p2);
+            backsub_phase<0>(n, r, wa1, wa2, lane, b0, b1, b2, p0, p1, p2);
             if (lane < n) x[lane] = b0;
             if (lane + 32 < n) x[lane + 32] = b1;
             if (lane + 64 < n) x[lane + 64] = b2;
@@ -1096,13 +1109,22 @@ __device__ void r1updt_g(int n, double *s, const double *u, double *v, double *w
         double wi = (i == n - 1) ? s[rowstart(n, n - 1)] : 0.;
         const int jtop = (i < n - 1 ? i : n - 2);
         int l = rowstart(n, jtop) + (i - jtop);                // S(j, i) in the packed rows, one row up per step
-        for (int j = jtop; j >= 0; l -= n - j, --j) {
-            const double c = cs[j];
-            if (c > 1.5) continue;
-            const double sl = s[l];
-            s[l] = c * sl - sn[j] * wi;
-            wi = sn[j] * sl + c * wi;
+        // "no rotation" (c == 2) is a predicated no-op rather than a branch, and the operands of four steps are
+        // fetched before the dependent chain on wi runs through them
+        auto step = [&](double c, double sg, double sl, int at) {
+            const double ns = c * sl - sg * wi, nw = sg * sl + c * wi;
+            if (!(c > 1.5)) { s[at] = ns; wi = nw; }
+        };
+        int j = jtop;
+        for (; j >= 3; j -= 4) {
+            const int l0 = l, l1 = l0 - (n - j), l2 = l1 - (n - j + 1), l3 = l2 - (n - j + 2);
+            const double x0 = s[l0], x1 = s[l1], x2 = s[l2], x3 = s[l3];
+            const double ca = cs[j], cb = cs[j - 1], cc = cs[j - 2], cd = cs[j - 3];
+            const double sa = sn[j], sb = sn[j - 1], sc = sn[j - 2], sd = sn[j - 3];
+            step(ca, sa, x0, l0); step(cb, sb, x1, l1); step(cc, sc, x2, l2); step(cd, sd, x3, l3);
+            l = l3 - (n - j + 3);
         }
+        for (; j >= 0; l -= n - j, --j) step(cs[j], sn[j], s[l], l);
         w[i] = wi + v[n - 1] * u[i];                 // add the spike from the rank-1 update
     }
     gsync<G>();
