@@ -113,13 +113,16 @@ SOCP_DEV double warp_max_d(double v) {
 // of by running rescaling, so nothing is sequential.  Every lane returns the same value.
 SOCP_DEV double enorm_warp(int n, const double *x) {
     const double rdwarf = 3.834e-20, rgiant = 1.304e19;
-    const double agiant = rgiant / (double)n;
+    // MINPACK's agiant = rgiant / n; the range test is written xabs * n < rgiant so that no call pays a
+    // divide (the two differ only for a component within an ulp of the threshold, where either
+    // accumulation is safe)
+    const double dn = (double)n;
     const int lane = threadIdx.x & 31;
     double s2 = 0., small_max = 0., big_max = 0.;
     bool isnan_ = false;
     for (int i = lane; i < n; i += 32) {
         const double xabs = fabs(x[i]);
-        if (xabs > rdwarf && xabs < agiant) s2 = fma(xabs, xabs, s2);
+        if (xabs > rdwarf && xabs * dn < rgiant) s2 = fma(xabs, xabs, s2);
         else if (xabs <= rdwarf) small_max = fmax(small_max, xabs);
         else if (xabs == xabs) big_max = fmax(big_max, xabs);
         else isnan_ = true;
@@ -132,7 +135,7 @@ SOCP_DEV double enorm_warp(int n, const double *x) {
     double s1 = 0., s3 = 0.;
     for (int i = lane; i < n; i += 32) {
         const double xabs = fabs(x[i]);
-        if (xabs > rdwarf && xabs < agiant) continue;
+        if (xabs > rdwarf && xabs * dn < rgiant) continue;
         if (xabs <= rdwarf) { if (xabs != 0.) { const double q = xabs / x3max; s3 = fma(q, q, s3); } }
         else { const double q = xabs / x1max; s1 = fma(q, q, s1); }
     }
@@ -732,6 +735,18 @@ SOCP_DEV double dot4(const double *a, const double *b, int m) {
     return (s0 + s1) + (s2 + s3);
 }
 
+// y[i] -= t * x[i] with the operands of four elements fetched before the first store (x and y never
+// overlap here, which the compiler cannot know: the plain loop serialises load -> FMA -> store per element)
+SOCP_DEV void axpy_sub4(double *y, const double *x, double t, int m) {
+    int i = 0;
+    for (; i + 3 < m; i += 4) {
+        const double x0 = x[i], x1 = x[i + 1], x2 = x[i + 2], x3 = x[i + 3];
+        const double y0 = y[i], y1 = y[i + 1], y2 = y[i + 2], y3 = y[i + 3];
+        y[i] = y0 - t * x0; y[i + 1] = y1 - t * x1; y[i + 2] = y2 - t * x2; y[i + 3] = y3 - t * x3;
+    }
+    for (; i < m; ++i) y[i] -= t * x[i];
+}
+
 // qrfac (no pivoting) fused with "qtf = Q^T fvec" (the Householder reflections are applied to
 // qtf as one more column); rdiag/acnorm as in MINPACK.  One thread per column.
 // Both routines skip work on EXACT zeros: hi[k] is the last row of column k that is not an exact zero
@@ -777,7 +792,7 @@ __device__ void qrfac_g(int n, double *a, int lda, double *rdiag, double *acnorm
                 const double sum = dot4(cj + j, ck + j, len);
                 if (sum != 0.) {
                     const double temp = sum / ajj;
-                    for (int i = j; i <= hj; ++i) ck[i] -= temp * cj[i];
+                    axpy_sub4(ck + j, cj + j, temp, len);
                     if (hi[k] < hj) hi[k] = hj;
                 }
             }
@@ -819,7 +834,7 @@ __device__ void qform_g(int n, double *q, int lda, double *wa, int rot, const in
                 const double sum = dot4(cj + k, wa + k, len);
                 if (sum != 0.) {
                     const double temp = sum / wk;
-                    for (int i = k; i <= hk; ++i) cj[i] -= temp * wa[i];
+                    axpy_sub4(cj + k, wa + k, temp, len);
                 }
             }
         }
