@@ -31,9 +31,9 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 FLOPS_PER_RK4_STEP = {"goddard": 1100.0}     # SURVEY.md 8(d) / BASELINE.md section 3 (nominal count)
 # DRAM traffic of hybrd_res_kernel per Broyden iteration of one problem, from the `ncu --set full` capture
-# profiles/r1_final_ncu_res_raw.csv: (dram__bytes_read.sum + dram__bytes_write.sum) = 664.3 MB for the 3592
+# profiles/r1_final_ncu_res_raw.csv: (dram__bytes_read.sum + dram__bytes_write.sum) = 660.8 MB for the 3537
 # iterations of the captured launch (1.02x the algorithmic 182 KB: no wasted re-reads)
-NCU_DRAM_BYTES_PER_ITERATION = 664.3e6 / 3592
+NCU_DRAM_BYTES_PER_ITERATION = 660.8e6 / 3537
 METRIC = "shooting solves/sec (Goddard free-tf, M=6, P=85; RK4 steps/sec and % of FP64 roofline alongside)"
 
 
