@@ -1315,10 +1315,11 @@ SOCP_DEV double *group_smem(const SolverDev &D, int per_group_doubles) {
 }
 
 // ---- kernel 2b: problems whose residual arrived (first evaluation or trial point) ---------------
-// 3 CTAs/SM (167 registers): measured equal to 4 CTAs/SM at 128 registers and better than 5 (the
-// co-resident chains slow each other down), so the registers are worth more
+// 4 CTAs/SM: after the instruction-level pass the kernel fits 128 registers without spills and the fourth
+// co-resident problem is worth -12 % kernel time (before it, the 128-register build spilled and 3 CTAs/SM
+// at 167 registers measured the same; 5 CTAs/SM were worse -- DESIGN.md section 5)
 template <int G, bool STAGE_R>
-__global__ void __launch_bounds__(128, 3)
+__global__ void __launch_bounds__(128, 4)
 hybrd_res_kernel(SolverDev D, int cur, int per_group_doubles) {
     const int GROUPS = (G == 32) ? (int)(blockDim.x >> 5) : 1;
     const int grp = (G == 32) ? (threadIdx.x >> 5) : 0;

@@ -190,8 +190,11 @@ void launch_hybrd(socp_ctx *ctx, const SolverDev &D, int cur, int grid, int prof
         else if (sp.stage_r) launch_smem(hybrd_jac_kernel<32, true, false>, g, thr, sp.bytes_jac, ctx->stream, D, cur, sp.doubles_jac);
         else launch_smem(hybrd_jac_kernel<32, false, false>, g, thr, sp.bytes_jac, ctx->stream, D, cur, sp.doubles_jac);
     } else {
-        if (sp.stage_r) launch_smem(hybrd_res_kernel<128, true>, g, thr, sp.bytes_res, ctx->stream, D, cur, sp.doubles_res);
-        else launch_smem(hybrd_res_kernel<128, false>, g, thr, sp.bytes_res, ctx->stream, D, cur, sp.doubles_res);
+        // the round grid is 6 CTAs per SM (two waves of the 3-CTA/SM Jacobian phase); the Broyden phase holds
+        // 4 CTAs/SM (P = 85), so a full grid becomes 8 per SM: two full waves again
+        const int g_res = (g == D.sm_count * 6) ? D.sm_count * 8 : g;
+        if (sp.stage_r) launch_smem(hybrd_res_kernel<128, true>, g_res, thr, sp.bytes_res, ctx->stream, D, cur, sp.doubles_res);
+        else launch_smem(hybrd_res_kernel<128, false>, g_res, thr, sp.bytes_res, ctx->stream, D, cur, sp.doubles_res);
         if (prof_slot >= 0) cudaEventRecord(prof_event(ctx, kProfEv * prof_slot + 3), ctx->stream);
         if (sp.stage_q_jac && sp.jac_r_global)          // R straight to global memory: one more CTA per SM
             launch_smem(hybrd_jac_kernel<128, false, true>, g, thr, (size_t)(sp.doubles_jac - D.LR) * 8, ctx->stream, D, cur, sp.doubles_jac - D.LR);
