@@ -41,6 +41,10 @@ enum { SOCP_HOST = 0, SOCP_DEVICE = 1 };
  * or adaptive Dormand-Prince 5(4) (its -D_USE_BOOST build, odeTools.cpp:131-134) */
 enum { SOCP_RK4 = 0, SOCP_DOPRI5 = 1 };
 enum { SOCP_OK = 0, SOCP_ERR_ARG = -1, SOCP_ERR_CUDA = -2, SOCP_ERR_NOMEM = -3, SOCP_ERR_UNSUPPORTED = -4 };
+/* per-problem `info` values are MINPACK's (0 bad input, 1 converged, 2 maxfev, 3 xtol too small, 4/5 slow
+ * progress); one more value exists only here: the batch driver stopped (its round limit) while the problem
+ * was still iterating -- it cannot happen with the default round limit of maxfev + 8 */
+#define SOCP_INFO_UNFINISHED (-2)
 
 #define SOCP_MAX_NODES 64
 #define SOCP_MAX_DIM 7
@@ -83,6 +87,8 @@ typedef struct {
     double iterations;                         /* problem-iterations of hybrd_res_kernel (Broyden steps), device counter */
     double jac_evals;                          /* Jacobian factorisations of hybrd_jac_kernel, device counter */
     double dopri_steps;                        /* accepted Dormand-Prince steps of the adaptive integration kernels */
+    double qpass_ms;                           /* hybrd_qpass_kernel alone (included in advance_ms; 0 in the fused build) */
+    double res_evals;                          /* residual requests assembled (base + trial points), device counter */
 } socp_stats;
 
 /* ---- context ------------------------------------------------------------------------------ */
@@ -109,7 +115,8 @@ int socp_num_param(const socp_shape *shape);                   /* shooting.cpp:1
 /* obstacle table of the vtolUAV penalty map (src/maps/obstacle/obstacle.cpp:24-36): type 0 ellipsoid,
  * 1 box; pos/rad are [n][3], host pointers.  The table lives in constant memory of the DEVICE: it is
  * shared by every context of the process on that device (empty until first set; creating another
- * context does not reset it), and setting it waits for the calling context's stream only. */
+ * context does not reset it); setting it synchronises the whole DEVICE first (cudaDeviceSynchronize), so no
+ * kernel of another context can observe a half-written table. */
 int socp_set_obstacles(socp_ctx *ctx, int n, const double *type, const double *pos, const double *rad);
 
 /* ---- hot path ------------------------------------------------------------------------------ */

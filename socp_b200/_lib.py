@@ -26,7 +26,8 @@ class Stats(ctypes.Structure):
                 ("integrate_ms", ctypes.c_double), ("integrate_launches", ctypes.c_double),
                 ("advance_ms", ctypes.c_double), ("advance_launches", ctypes.c_double),
                 ("assemble_ms", ctypes.c_double), ("jac_ms", ctypes.c_double),
-                ("iterations", ctypes.c_double), ("jac_evals", ctypes.c_double), ("dopri_steps", ctypes.c_double)]
+                ("iterations", ctypes.c_double), ("jac_evals", ctypes.c_double), ("dopri_steps", ctypes.c_double),
+                ("qpass_ms", ctypes.c_double), ("res_evals", ctypes.c_double)]
 
 
 _LIB = None

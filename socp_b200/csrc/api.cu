@@ -54,9 +54,11 @@ struct socp_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int sm_count = 0;
     int profile = 0;
-    double integrate_ms = 0, integrate_launches = 0, advance_ms = 0, advance_launches = 0, assemble_ms = 0, jac_ms = 0;
+    double integrate_ms = 0, integrate_launches = 0, advance_ms = 0, advance_launches = 0, assemble_ms = 0, jac_ms = 0, qpass_ms = 0;
     std::vector<cudaEvent_t> prof_events;
     SolverWorkspace solver;              // persistent state of the batched solver (solver.cuh)
+    std::map<const void *, size_t> smem_configured;   // opt-in dynamic shared memory per kernel, on THIS device
+    int launch_error = 0;                // set by a failed launch configuration inside a solver round
 };
 
 #define CUDA_TRY(ctx, call)                                                              \
@@ -194,10 +196,16 @@ int socp_create(int device, socp_ctx **out) {
     cudaDeviceProp prop;
     cudaGetDeviceProperties(&prop, device);
     ctx->sm_count = prop.multiProcessorCount;
-    cudaMalloc(&ctx->d_counters, 64 * sizeof(unsigned long long));
-    cudaMemset(ctx->d_counters, 0, 64 * sizeof(unsigned long long));
-    cudaEventCreate(&ctx->ev0);
-    cudaEventCreate(&ctx->ev1);
+    // every allocation of the context is checked: a half-built context is destroyed, never returned
+    if ((e = cudaMalloc(&ctx->d_counters, 64 * sizeof(unsigned long long))) != cudaSuccess ||
+        (e = cudaMemset(ctx->d_counters, 0, 64 * sizeof(unsigned long long))) != cudaSuccess ||
+        (e = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) {
+        g_create_error = std::string("socp_create: ") + cudaGetErrorString(e);
+        const int code = (e == cudaErrorMemoryAllocation) ? SOCP_ERR_NOMEM : SOCP_ERR_CUDA;
+        cudaGetLastError();
+        socp_destroy(ctx);
+        return code;
+    }
     *out = ctx;
     return SOCP_OK;
 }
@@ -252,6 +260,8 @@ int socp_get_stats(socp_ctx *ctx, socp_stats *out) {
     out->iterations = (double)c[1];
     out->jac_evals = (double)c[2];
     out->dopri_steps = (double)c[3];
+    out->res_evals = (double)c[4];
+    out->qpass_ms = ctx->qpass_ms;
     if (getenv("SOCP_PHASE_CLOCKS")) {
         fprintf(stderr, "phase clocks (cycles): res");
         for (int k = 0; k < 8; ++k) fprintf(stderr, " %llu", c[16 + k]);
@@ -269,7 +279,7 @@ int socp_reset_stats(socp_ctx *ctx) {
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_counters, 0, 64 * sizeof(unsigned long long), ctx->stream));
     ctx->launches = 0;
     ctx->rounds = 0;
-    ctx->integrate_ms = ctx->integrate_launches = ctx->advance_ms = ctx->advance_launches = ctx->assemble_ms = ctx->jac_ms = 0;
+    ctx->integrate_ms = ctx->integrate_launches = ctx->advance_ms = ctx->advance_launches = ctx->assemble_ms = ctx->jac_ms = ctx->qpass_ms = 0;
     return SOCP_OK;
 }
 
@@ -300,7 +310,9 @@ int socp_set_obstacles(socp_ctx *ctx, int n, const double *type, const double *p
         for (int k = 0; k < 3; ++k) { tab[i * 7 + 1 + k] = pos[i * 3 + k]; tab[i * 7 + 4 + k] = rad[i * 3 + k]; }
     }
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    // the table is shared by every context of this device: wait for ALL of its streams, not only ours,
+    // so that no in-flight vtolUAV kernel of another context reads a half-updated table
+    CUDA_TRY(ctx, cudaDeviceSynchronize());
     if (n) CUDA_TRY(ctx, cudaMemcpyToSymbol(c_obstacles, tab, sizeof(double) * 7 * n));
     CUDA_TRY(ctx, cudaMemcpyToSymbol(c_num_obstacles, &n, sizeof(int)));
     return SOCP_OK;

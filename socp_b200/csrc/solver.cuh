@@ -57,7 +57,8 @@ struct SolverDev {
     // work lists, double buffered: list[2][2][B], count[2][2]
     int *lists;
     int *counts;
-    unsigned long long *counters;      // [0] RK4 steps, [1] Broyden iterations, [2] Jacobian factorisations, [16+k] / [32+k] phase clocks
+    unsigned long long *counters;      // [0] RK4 steps, [1] Broyden iterations, [2] Jacobian factorisations, [3] dopri steps,
+                                       // [4] residual requests, [16+k] / [32+k] phase clocks
     int sm_count;                      // multiprocessors of the device (seq_warp)
     int phase_clocks;                  // debugging aid (SOCP_PHASE_CLOCKS=1): accumulate clock64() per phase
 };
@@ -423,6 +424,7 @@ assemble_kernel(SolverDev D, int cur) {
     const int *jac_list = D.lists + (size_t)(cur * 2 + 1) * D.B;
     const int n = D.P;
     const long total = (long)nres + (long)njac * n;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && nres > 0) atomicAdd(D.counters + 4, (unsigned long long)nres);
     for (long w = (long)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += (long)gridDim.x * blockDim.x) {
         if (w < nres) {
             const long b = res_list[w];
@@ -1650,8 +1652,9 @@ __global__ void solver_finish(SolverDev D, long first, double *x_out, double *fv
     if (fjac_out && i < D.B * (long)D.P * D.P) fjac_out[first * (long)D.P * D.P + i] = D.fjac[i];
     if (i < D.B) {
         const int *is = D.istate + i * I_COUNT;
-        // a problem still in flight when the round limit is hit reports info 2-like "not finished"
-        if (info) info[first + i] = (is[I_PHASE] == PH_IDLE) ? is[I_INFO] : 2;
+        // a problem still in flight when the round limit is hit is NOT a hybrd outcome: it gets its own code
+        // (SOCP_INFO_UNFINISHED, negative like hybrd's user-abort codes), distinct from a genuine maxfev (2)
+        if (info) info[first + i] = (is[I_PHASE] == PH_IDLE) ? is[I_INFO] : SOCP_INFO_UNFINISHED;
         if (nfev) nfev[first + i] = is[I_NFEV];
         if (njev) njev[first + i] = is[I_NJEV];
         if (fnorm) fnorm[first + i] = D.dstate[i * D_COUNT + D_FNORM];

@@ -167,15 +167,25 @@ SmemPlan smem_plan(const SolverDev &D) {
     return p;
 }
 
+// Opt-in dynamic shared memory is a per-DEVICE function attribute: the size already configured is kept per
+// context (one context = one device), never process-wide, so a second context on another GPU of the same
+// process configures its own copy and two host threads never share the table.
 template <typename K>
-void launch_smem(K kernel, int grid, int threads, size_t smem, cudaStream_t st, const SolverDev &D, int cur, int doubles) {
-    static std::map<const void *, size_t> configured;      // opt-in shared memory per kernel
-    size_t &have = configured[(const void *)kernel];
-    if (smem > 48 * 1024 && smem > have) {
-        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        have = smem;
+int launch_smem(socp_ctx *ctx, K kernel, int grid, int threads, size_t smem, const SolverDev &D, int cur, int doubles) {
+    if (smem > 48 * 1024) {
+        size_t &have = ctx->smem_configured[(const void *)kernel];
+        if (smem > have) {
+            cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) {
+                ctx->err = std::string("cudaFuncSetAttribute(MaxDynamicSharedMemorySize): ") + cudaGetErrorString(e);
+                ctx->launch_error = SOCP_ERR_CUDA;
+                return SOCP_ERR_CUDA;
+            }
+            have = smem;
+        }
     }
-    kernel<<<grid, threads, smem, st>>>(D, cur, doubles);
+    kernel<<<grid, threads, smem, ctx->stream>>>(D, cur, doubles);
+    return SOCP_OK;
 }
 
 void launch_hybrd(socp_ctx *ctx, const SolverDev &D, int cur, int grid, int prof_slot) {
@@ -183,24 +193,24 @@ void launch_hybrd(socp_ctx *ctx, const SolverDev &D, int cur, int grid, int prof
     const int thr = (sp.G == 32) ? 32 * sp.groups : 128;
     const int g = (sp.G == 32) ? grid * (4 / sp.groups) : grid;
     if (sp.G == 32) {
-        if (sp.stage_r) launch_smem(hybrd_res_kernel<32, true>, g, thr, sp.bytes_res, ctx->stream, D, cur, sp.doubles_res);
-        else launch_smem(hybrd_res_kernel<32, false>, g, thr, sp.bytes_res, ctx->stream, D, cur, sp.doubles_res);
+        if (sp.stage_r) launch_smem(ctx, hybrd_res_kernel<32, true>, g, thr, sp.bytes_res, D, cur, sp.doubles_res);
+        else launch_smem(ctx, hybrd_res_kernel<32, false>, g, thr, sp.bytes_res, D, cur, sp.doubles_res);
         if (prof_slot >= 0) cudaEventRecord(prof_event(ctx, kProfEv * prof_slot + 3), ctx->stream);
-        if (sp.stage_q_jac) launch_smem(hybrd_jac_kernel<32, true, true>, g, thr, sp.bytes_jac, ctx->stream, D, cur, sp.doubles_jac);
-        else if (sp.stage_r) launch_smem(hybrd_jac_kernel<32, true, false>, g, thr, sp.bytes_jac, ctx->stream, D, cur, sp.doubles_jac);
-        else launch_smem(hybrd_jac_kernel<32, false, false>, g, thr, sp.bytes_jac, ctx->stream, D, cur, sp.doubles_jac);
+        if (sp.stage_q_jac) launch_smem(ctx, hybrd_jac_kernel<32, true, true>, g, thr, sp.bytes_jac, D, cur, sp.doubles_jac);
+        else if (sp.stage_r) launch_smem(ctx, hybrd_jac_kernel<32, true, false>, g, thr, sp.bytes_jac, D, cur, sp.doubles_jac);
+        else launch_smem(ctx, hybrd_jac_kernel<32, false, false>, g, thr, sp.bytes_jac, D, cur, sp.doubles_jac);
     } else {
         // the round grid is 6 CTAs per SM (two waves of the 3-CTA/SM Jacobian phase); the Broyden phase holds
         // 4 CTAs/SM (P = 85), so a full grid becomes 8 per SM: two full waves again
         const int g_res = (g == D.sm_count * 6) ? D.sm_count * 8 : g;
-        if (sp.stage_r) launch_smem(hybrd_res_kernel<128, true>, g_res, thr, sp.bytes_res, ctx->stream, D, cur, sp.doubles_res);
-        else launch_smem(hybrd_res_kernel<128, false>, g_res, thr, sp.bytes_res, ctx->stream, D, cur, sp.doubles_res);
+        if (sp.stage_r) launch_smem(ctx, hybrd_res_kernel<128, true>, g_res, thr, sp.bytes_res, D, cur, sp.doubles_res);
+        else launch_smem(ctx, hybrd_res_kernel<128, false>, g_res, thr, sp.bytes_res, D, cur, sp.doubles_res);
         if (prof_slot >= 0) cudaEventRecord(prof_event(ctx, kProfEv * prof_slot + 3), ctx->stream);
         if (sp.stage_q_jac && sp.jac_r_global)          // R straight to global memory: one more CTA per SM
-            launch_smem(hybrd_jac_kernel<128, false, true>, g, thr, (size_t)(sp.doubles_jac - D.LR) * 8, ctx->stream, D, cur, sp.doubles_jac - D.LR);
-        else if (sp.stage_q_jac) launch_smem(hybrd_jac_kernel<128, true, true>, g, thr, sp.bytes_jac, ctx->stream, D, cur, sp.doubles_jac);
-        else if (sp.stage_r) launch_smem(hybrd_jac_kernel<128, true, false>, g, thr, sp.bytes_jac, ctx->stream, D, cur, sp.doubles_jac);
-        else launch_smem(hybrd_jac_kernel<128, false, false>, g, thr, sp.bytes_jac, ctx->stream, D, cur, sp.doubles_jac);
+            launch_smem(ctx, hybrd_jac_kernel<128, false, true>, g, thr, (size_t)(sp.doubles_jac - D.LR) * 8, D, cur, sp.doubles_jac - D.LR);
+        else if (sp.stage_q_jac) launch_smem(ctx, hybrd_jac_kernel<128, true, true>, g, thr, sp.bytes_jac, D, cur, sp.doubles_jac);
+        else if (sp.stage_r) launch_smem(ctx, hybrd_jac_kernel<128, true, false>, g, thr, sp.bytes_jac, D, cur, sp.doubles_jac);
+        else launch_smem(ctx, hybrd_jac_kernel<128, false, false>, g, thr, sp.bytes_jac, D, cur, sp.doubles_jac);
     }
 }
 
@@ -257,8 +267,11 @@ int run_solver(socp_ctx *ctx, const socp_shape *shape, long B, const double *d_m
     size_t free_b = 0, total_b = 0;
     CUDA_TRY(ctx, cudaMemGetInfo(&free_b, &total_b));
     const size_t budget = (size_t)((free_b + ctx->solver.cap) * 0.85);
-    long wave = (long)std::min<size_t>((size_t)B, std::max<size_t>(1, (budget - (1 << 20)) / pl.bytes_per_problem));
-    if (wave < 1) return fail(ctx, SOCP_ERR_NOMEM, "not enough device memory for one problem");
+    const size_t reserve = (size_t)1 << 20;
+    if (budget < reserve + pl.bytes_per_problem)
+        return fail(ctx, SOCP_ERR_NOMEM, "not enough device memory for one problem (" + std::to_string(pl.bytes_per_problem) +
+                                         " bytes per problem, " + std::to_string(free_b) + " free)");
+    const long wave = (long)std::min<size_t>((size_t)B, (budget - reserve) / pl.bytes_per_problem);
     size_t need = carve(pl, nullptr, wave);
     if (need > ctx->solver.cap) {
         if (ctx->solver.blob) cudaFree(ctx->solver.blob);
@@ -318,6 +331,13 @@ int run_solver(socp_ctx *ctx, const socp_shape *shape, long B, const double *d_m
             const int gi = (int)std::max<long>(1, std::min<long>(grid_int, (items + 127) / 128));
             const int ga = (int)std::max<long>(1, std::min<long>(grid_adv, live));
             launch_round_any(ctx, D, cur, gi, ga, ctx->profile ? pending : -1);
+            if (ctx->launch_error) {                   // a launch could not be configured: nothing of this round ran
+                const int code = ctx->launch_error;
+                ctx->launch_error = 0;
+                cudaStreamSynchronize(ctx->stream);
+                if (round_log) fclose(round_log);
+                return code;
+            }
             ++pending;
             cur = 1 - cur;
             if (run_mode == RUN_SOLVE && (round % check_every) == check_every - 1) {
@@ -352,6 +372,13 @@ int check_problem_args(socp_ctx *ctx, const socp_shape *shape, long B, const voi
     return SOCP_OK;
 }
 
+// error return after host buffers may have been staged: no asynchronous copy from (or to) a caller buffer
+// is left in flight when the call returns an error
+int bail(socp_ctx *ctx, int rc) {
+    if (ctx) cudaStreamSynchronize(ctx->stream);
+    return rc;
+}
+
 }  // namespace
 
 extern "C" {
@@ -367,9 +394,9 @@ int socp_residual_batch(socp_ctx *ctx, const socp_shape *shape, long B, const do
     const double *d_Xb = stage_in(ctx, SLOT_XB, Xb, (size_t)B * (M + 1) * dim, mem, &rc);
     const double *d_x = stage_in(ctx, SLOT_X, x, (size_t)B * P, mem, &rc);
     double *d_f = stage_out(ctx, SLOT_FVEC, fvec, (size_t)B * P, mem, &rc);
-    if (rc != SOCP_OK) return rc;
+    if (rc != SOCP_OK) return bail(ctx, rc);
     rc = run_solver(ctx, shape, B, d_mp, d_time, d_Xb, d_x, RUN_RESIDUAL, 0., 1, 1e-15, nullptr, d_f, nullptr, nullptr, nullptr, nullptr);
-    if (rc != SOCP_OK) return rc;
+    if (rc != SOCP_OK) return bail(ctx, rc);
     if ((rc = fetch_out(ctx, fvec, d_f, (size_t)B * P, mem)) != SOCP_OK) return rc;
     if (mem == SOCP_HOST) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return SOCP_OK;
@@ -387,9 +414,9 @@ int socp_fdjac_batch(socp_ctx *ctx, const socp_shape *shape, long B, const doubl
     const double *d_Xb = stage_in(ctx, SLOT_XB, Xb, (size_t)B * (M + 1) * dim, mem, &rc);
     const double *d_x = stage_in(ctx, SLOT_X, x, (size_t)B * P, mem, &rc);
     double *d_j = stage_out(ctx, SLOT_FJAC, fjac, (size_t)B * P * P, mem, &rc);
-    if (rc != SOCP_OK) return rc;
+    if (rc != SOCP_OK) return bail(ctx, rc);
     rc = run_solver(ctx, shape, B, d_mp, d_time, d_Xb, d_x, RUN_FDJAC, 0., 1, epsfcn, nullptr, nullptr, d_j, nullptr, nullptr, nullptr);
-    if (rc != SOCP_OK) return rc;
+    if (rc != SOCP_OK) return bail(ctx, rc);
     if ((rc = fetch_out(ctx, fjac, d_j, (size_t)B * P * P, mem)) != SOCP_OK) return rc;
     if (mem == SOCP_HOST) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return SOCP_OK;
@@ -399,10 +426,15 @@ int socp_solve_batch(socp_ctx *ctx, const socp_shape *shape, long B, const doubl
                      const double *time, const double *Xb, double *x, double xtol, int maxfev,
                      int *info, int *nfev, double *fnorm, int mem) {
     int rc = check_problem_args(ctx, shape, B, mparams, time, Xb, x, info);
-    if (rc != SOCP_OK) return rc;
+    if (rc != SOCP_OK) return bail(ctx, rc);
     if (xtol < 0. || maxfev <= 0) {
         // hybrd's own argument check: info = 0 and x untouched (MINPACK hybrd, "check the input parameters")
         if (mem == SOCP_HOST) for (long b = 0; b < B; ++b) { info[b] = 0; if (nfev) nfev[b] = 0; }
+        else if (B > 0) {      // device buffers: the same values, stream-ordered
+            cudaSetDevice(ctx->device);
+            cudaMemsetAsync(info, 0, sizeof(int) * (size_t)B, ctx->stream);
+            if (nfev) cudaMemsetAsync(nfev, 0, sizeof(int) * (size_t)B, ctx->stream);
+        }
         return fail(ctx, SOCP_ERR_ARG, "xtol < 0 or maxfev <= 0");
     }
     if (B == 0) return SOCP_OK;
@@ -416,9 +448,9 @@ int socp_solve_batch(socp_ctx *ctx, const socp_shape *shape, long B, const doubl
     int *d_info = stage_out(ctx, SLOT_INFO, info, (size_t)B, mem, &rc);
     int *d_nfev = stage_out(ctx, SLOT_NFEV, nfev, (size_t)B, mem, &rc);
     double *d_fn = stage_out(ctx, SLOT_FNORM, fnorm, (size_t)B, mem, &rc);
-    if (rc != SOCP_OK) return rc;
+    if (rc != SOCP_OK) return bail(ctx, rc);
     rc = run_solver(ctx, shape, B, d_mp, d_time, d_Xb, d_xin, RUN_SOLVE, xtol, maxfev, 1e-15, d_x, nullptr, nullptr, d_info, d_nfev, d_fn);
-    if (rc != SOCP_OK) return rc;
+    if (rc != SOCP_OK) return bail(ctx, rc);
     if ((rc = fetch_out(ctx, x, d_x, (size_t)B * P, mem)) != SOCP_OK) return rc;
     if ((rc = fetch_out(ctx, info, d_info, (size_t)B, mem)) != SOCP_OK) return rc;
     if ((rc = fetch_out(ctx, nfev, d_nfev, (size_t)B, mem)) != SOCP_OK) return rc;
@@ -431,9 +463,15 @@ int socp_solve_hybrj_batch(socp_ctx *ctx, const socp_shape *shape, long B, const
                            const double *time, const double *Xb, double *x, double xtol, int maxfev,
                            int *info, int *nfev, int *njev, double *fnorm, int mem) {
     int rc = check_problem_args(ctx, shape, B, mparams, time, Xb, x, info);
-    if (rc != SOCP_OK) return rc;
+    if (rc != SOCP_OK) return bail(ctx, rc);
     if (xtol < 0. || maxfev <= 0) {
         if (mem == SOCP_HOST) for (long b = 0; b < B; ++b) { info[b] = 0; if (nfev) nfev[b] = 0; if (njev) njev[b] = 0; }
+        else if (B > 0) {
+            cudaSetDevice(ctx->device);
+            cudaMemsetAsync(info, 0, sizeof(int) * (size_t)B, ctx->stream);
+            if (nfev) cudaMemsetAsync(nfev, 0, sizeof(int) * (size_t)B, ctx->stream);
+            if (njev) cudaMemsetAsync(njev, 0, sizeof(int) * (size_t)B, ctx->stream);
+        }
         return fail(ctx, SOCP_ERR_ARG, "xtol < 0 or maxfev <= 0");
     }
     if (B == 0) return SOCP_OK;
@@ -448,9 +486,9 @@ int socp_solve_hybrj_batch(socp_ctx *ctx, const socp_shape *shape, long B, const
     int *d_nfev = stage_out(ctx, SLOT_NFEV, nfev, (size_t)B, mem, &rc);
     int *d_njev = stage_out(ctx, SLOT_AUX0, njev, (size_t)B, mem, &rc);
     double *d_fn = stage_out(ctx, SLOT_FNORM, fnorm, (size_t)B, mem, &rc);
-    if (rc != SOCP_OK) return rc;
+    if (rc != SOCP_OK) return bail(ctx, rc);
     rc = run_solver(ctx, shape, B, d_mp, d_time, d_Xb, d_xin, RUN_SOLVE, xtol, maxfev, 1e-15, d_x, nullptr, nullptr, d_info, d_nfev, d_fn, 1, d_njev);
-    if (rc != SOCP_OK) return rc;
+    if (rc != SOCP_OK) return bail(ctx, rc);
     if ((rc = fetch_out(ctx, x, d_x, (size_t)B * P, mem)) != SOCP_OK) return rc;
     if ((rc = fetch_out(ctx, info, d_info, (size_t)B, mem)) != SOCP_OK) return rc;
     if ((rc = fetch_out(ctx, nfev, d_nfev, (size_t)B, mem)) != SOCP_OK) return rc;
@@ -471,9 +509,9 @@ int socp_jacobian_batch(socp_ctx *ctx, const socp_shape *shape, long B, const do
     const double *d_Xb = stage_in(ctx, SLOT_XB, Xb, (size_t)B * (M + 1) * dim, mem, &rc);
     const double *d_x = stage_in(ctx, SLOT_X, x, (size_t)B * P, mem, &rc);
     double *d_j = stage_out(ctx, SLOT_FJAC, fjac, (size_t)B * P * P, mem, &rc);
-    if (rc != SOCP_OK) return rc;
+    if (rc != SOCP_OK) return bail(ctx, rc);
     rc = run_solver(ctx, shape, B, d_mp, d_time, d_Xb, d_x, RUN_FDJAC, 0., 1, 1e-15, nullptr, nullptr, d_j, nullptr, nullptr, nullptr, 1, nullptr);
-    if (rc != SOCP_OK) return rc;
+    if (rc != SOCP_OK) return bail(ctx, rc);
     if ((rc = fetch_out(ctx, fjac, d_j, (size_t)B * P * P, mem)) != SOCP_OK) return rc;
     if (mem == SOCP_HOST) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return SOCP_OK;
@@ -496,7 +534,7 @@ int socp_traj_var_batch(socp_ctx *ctx, int model_id, int step_nbr, long B, const
     const double *d_tf = stage_in(ctx, SLOT_TF, tf, (size_t)B, mem, &rc);
     const double *d_X0 = stage_in(ctx, SLOT_X0, X0, (size_t)B * NV, mem, &rc);
     double *d_Xf = stage_out(ctx, SLOT_XF, Xf, (size_t)B * NV, mem, &rc);
-    if (rc != SOCP_OK) return rc;
+    if (rc != SOCP_OK) return bail(ctx, rc);
     const long threads = B * 16;
     traj_var_kernel<DOUBLE_INTEGRATOR><<<(unsigned)((threads + 127) / 128), 128, 0, ctx->stream>>>(B, S, d_mp, d_t0, d_tf, d_X0, d_Xf, ctx->d_counters);
     ctx->launches += 1;
@@ -515,7 +553,7 @@ int socp_continuation_param_batch(socp_ctx *ctx, const socp_shape *shape, long B
                                   int maxfev, double step, int param_idx, const double *goal,
                                   double step_min, int *info, int *calls) {
     int rc = check_problem_args(ctx, shape, B, mparams, time, Xb, x, info);
-    if (rc != SOCP_OK) return rc;
+    if (rc != SOCP_OK) return bail(ctx, rc);
     const int P = socp_num_param(shape), dim = kDim[shape->model_id], np = kNP[shape->model_id], M = shape->num_multi;
     if (param_idx < 0 || param_idx >= np || !goal) return fail(ctx, SOCP_ERR_ARG, "bad parameter index / goal");
     if (step <= 0) step = 1.0;                              // shooting.cpp:352-355
@@ -548,7 +586,7 @@ int socp_continuation_param_batch(socp_ctx *ctx, const socp_shape *shape, long B
         }
         rc = socp_solve_batch(ctx, shape, A, wmp.data(), wtime.data(), wXb.data(), wx.data(), xtol, maxfev,
                               winfo.data(), wnfev.data(), wfn.data(), SOCP_HOST);
-        if (rc != SOCP_OK) return rc;
+        if (rc != SOCP_OK) return bail(ctx, rc);
         for (long a = 0; a < A; ++a) {
             const long k = idx[a];
             const int ret = winfo[a];
@@ -582,7 +620,7 @@ int socp_continuation_boundary_batch(socp_ctx *ctx, const socp_shape *shape, lon
                                      const double *Xb_des, double *x, double xtol, int maxfev,
                                      double step, double step_min, int *info, int *calls) {
     int rc = check_problem_args(ctx, shape, B, mparams, time_prec, Xb_prec, x, info);
-    if (rc != SOCP_OK) return rc;
+    if (rc != SOCP_OK) return bail(ctx, rc);
     if (!time_des || !Xb_des) return fail(ctx, SOCP_ERR_ARG, "NULL desired boundary data");
     const int P = socp_num_param(shape), dim = kDim[shape->model_id], np = kNP[shape->model_id], M = shape->num_multi;
     const int nt = M + 1, nx = (M + 1) * dim;
@@ -615,7 +653,7 @@ int socp_continuation_boundary_batch(socp_ctx *ctx, const socp_shape *shape, lon
         }
         rc = socp_solve_batch(ctx, shape, A, wmp.data(), wtime.data(), wXb.data(), wx.data(), xtol, maxfev,
                               winfo.data(), wnfev.data(), wfn.data(), SOCP_HOST);
-        if (rc != SOCP_OK) return rc;
+        if (rc != SOCP_OK) return bail(ctx, rc);
         for (long a = 0; a < A; ++a) {
             const long k = idx[a];
             const int ret = winfo[a];

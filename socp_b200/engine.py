@@ -77,30 +77,44 @@ def _is_torch(a):
 
 
 class _Arg:
-    """Resolve an array argument to (pointer, keepalive) for host or device memory."""
+    """Resolve an array argument to (pointer, keepalive) for host or device memory.  Device tensors are
+    checked before their pointer crosses the C ABI (dtype, contiguity, device): the library reinterprets
+    the memory as float64 / int32 on the engine's GPU."""
 
-    def __init__(self, mem):
+    def __init__(self, mem, device=None):
         self.mem = mem
+        self.device = device
         self.keep = []
+
+    def _device_ptr(self, a, dtype):
+        import torch
+        want = {np.float64: torch.float64, np.int32: torch.int32}[dtype]
+        if not _is_torch(a) or not a.is_cuda:
+            raise ValueError("device mode needs torch CUDA tensors for every array argument")
+        if a.dtype != want:
+            raise ValueError("device tensor has dtype %s, the library reads %s" % (a.dtype, want))
+        if not a.is_contiguous():
+            raise ValueError("device tensors must be contiguous")
+        if self.device is not None and a.device.index != self.device:
+            raise ValueError("tensor lives on cuda:%s, the engine on cuda:%s" % (a.device.index, self.device))
+        return ctypes.c_void_p(a.data_ptr())
 
     def inp(self, a, dtype=np.float64):
         if a is None:
             return None
         if self.mem == DEVICE:
-            if not _is_torch(a) or not a.is_cuda or not a.is_contiguous():
-                raise ValueError("device mode needs contiguous torch CUDA tensors")
-            return ctypes.c_void_p(a.data_ptr())
+            return self._device_ptr(a, dtype)
         arr = np.ascontiguousarray(a, dtype=dtype)
         self.keep.append(arr)
         return ctypes.c_void_p(arr.ctypes.data)
 
-    def out(self, a):
+    def out(self, a, dtype=np.float64):
         if a is None:
             return None
         if self.mem == DEVICE:
-            return ctypes.c_void_p(a.data_ptr())
-        if not (isinstance(a, np.ndarray) and a.flags["C_CONTIGUOUS"]):
-            raise ValueError("output buffers must be contiguous numpy arrays")
+            return self._device_ptr(a, dtype)
+        if not (isinstance(a, np.ndarray) and a.flags["C_CONTIGUOUS"] and a.dtype == np.dtype(dtype)):
+            raise ValueError("output buffers must be contiguous numpy arrays of dtype %s" % np.dtype(dtype))
         return ctypes.c_void_p(a.ctypes.data)
 
 
@@ -114,7 +128,8 @@ class Engine:
         if rc != 0:
             raise SocpError("socp_create failed: %s" % self._L.socp_last_error(None).decode())
         self._h = h
-        self.device = device
+        self.device = int(device)
+        self._bound_stream = None
 
     def close(self):
         if getattr(self, "_h", None):
@@ -133,8 +148,20 @@ class Engine:
 
     # -- plumbing -------------------------------------------------------------------------------
     def use_torch_stream(self):
+        """Run on torch's current stream of the engine's device.  DEVICE-mode calls do this by themselves
+        (see _arg), so tensors produced on torch's stream are ordered before the library reads them."""
         import torch
-        self._check(self._L.socp_set_stream(self._h, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        if st != self._bound_stream:
+            self._check(self._L.socp_set_stream(self._h, ctypes.c_void_p(st)))
+            self._bound_stream = st
+
+    def _arg(self, mem):
+        """Argument resolver of one call.  In DEVICE mode the engine first binds to torch's CURRENT stream:
+        the library then reads and writes the tensors in stream order with whatever produced them."""
+        if mem == DEVICE:
+            self.use_torch_stream()
+        return _Arg(mem, self.device)
 
     def sync(self):
         self._check(self._L.socp_sync(self._h))
@@ -145,7 +172,9 @@ class Engine:
         return dict(rk4_steps=s.rk4_steps, kernel_launches=s.kernel_launches,
                     solver_rounds=s.solver_rounds, device_bytes=s.device_bytes,
                     integrate_ms=s.integrate_ms, integrate_launches=s.integrate_launches,
-                    advance_ms=s.advance_ms, advance_launches=s.advance_launches, assemble_ms=s.assemble_ms, jac_ms=s.jac_ms, iterations=s.iterations, jac_evals=s.jac_evals, dopri_steps=s.dopri_steps)
+                    advance_ms=s.advance_ms, advance_launches=s.advance_launches, assemble_ms=s.assemble_ms, jac_ms=s.jac_ms, iterations=s.iterations, jac_evals=s.jac_evals,
+                    dopri_steps=s.dopri_steps, qpass_ms=s.qpass_ms, res_evals=s.res_evals,
+                    res_ms=s.advance_ms - s.jac_ms)
 
     def set_profiling(self, on=True):
         self._check(self._L.socp_set_profiling(self._h, int(bool(on))))
@@ -202,7 +231,7 @@ class Engine:
         elif out is None:
             import torch
             out = torch.empty_like(X0)
-        a = _Arg(mem)
+        a = self._arg(mem)
         self._check(self._L.socp_traj_batch(self._h, model_id, int(step_nbr or 0), B, a.inp(mparams), a.inp(sw),
                                             a.inp(t0), a.inp(tf), a.inp(X0), a.out(out), mem))
         return out
@@ -218,7 +247,7 @@ class Engine:
         Xf, ns = np.empty((B, N)), np.zeros((B, 2), dtype=np.int32)
         a = _Arg(HOST)
         self._check(self._L.socp_traj_adaptive_batch(self._h, model_id, int(step_nbr or 0), B, a.inp(mparams), a.inp(sw),
-                                                     a.inp(t0), a.inp(tf), a.inp(X0), float(tol), a.out(Xf), a.out(ns), HOST))
+                                                     a.inp(t0), a.inp(tf), a.inp(X0), float(tol), a.out(Xf), a.out(ns, np.int32), HOST))
         return Xf, ns
 
     def trace_batch(self, model_id, mparams, t0, X0, tf, step_nbr=0, sw=None):
@@ -234,7 +263,7 @@ class Engine:
         rows, nrows, Xf = np.zeros((B, R, W)), np.zeros(B, dtype=np.int32), np.empty((B, N))
         a = _Arg(HOST)
         self._check(self._L.socp_trace_batch(self._h, model_id, int(step_nbr or 0), B, a.inp(mparams), a.inp(sw),
-                                             a.inp(t0), a.inp(tf), a.inp(X0), a.out(rows), a.out(nrows), a.out(Xf), HOST))
+                                             a.inp(t0), a.inp(tf), a.inp(X0), a.out(rows), a.out(nrows, np.int32), a.out(Xf), HOST))
         return rows, nrows, Xf
 
     def point_batch(self, model_id, mparams, t, X, sw=None, chart_stage=None):
@@ -267,7 +296,7 @@ class Engine:
             else:
                 import torch
                 out = torch.empty_like(x)
-        a = _Arg(mem)
+        a = self._arg(mem)
         self._check(self._L.socp_residual_batch(self._h, ctypes.byref(shape), B, a.inp(mparams), a.inp(time),
                                                 a.inp(Xb), a.inp(x), a.out(out), mem))
         return out
@@ -299,10 +328,10 @@ class Engine:
             info = torch.empty(B, dtype=torch.int32, device=x.device) if info is None else info
             nfev = torch.empty(B, dtype=torch.int32, device=x.device) if nfev is None else nfev
             fnorm = torch.empty(B, dtype=torch.float64, device=x.device) if fnorm is None else fnorm
-        a = _Arg(mem)
+        a = self._arg(mem)
         self._check(self._L.socp_solve_batch(self._h, ctypes.byref(shape), B, a.inp(mparams), a.inp(time),
-                                             a.inp(Xb), a.out(x), float(xtol), int(maxfev), a.out(info),
-                                             a.out(nfev), a.out(fnorm), mem))
+                                             a.inp(Xb), a.out(x), float(xtol), int(maxfev), a.out(info, np.int32),
+                                             a.out(nfev, np.int32), a.out(fnorm), mem))
         return dict(x=x, info=info, nfev=nfev, fnorm=fnorm)
 
     # -- analytic-Jacobian path (modelOrder == 1; the double integrator, as in the reference) -----
@@ -338,8 +367,8 @@ class Engine:
         fnorm = np.empty(B)
         a = _Arg(HOST)
         self._check(self._L.socp_solve_hybrj_batch(self._h, ctypes.byref(shape), B, a.inp(mparams), a.inp(time),
-                                                   a.inp(Xb), a.out(x), float(xtol), int(maxfev), a.out(info),
-                                                   a.out(nfev), a.out(njev), a.out(fnorm), HOST))
+                                                   a.inp(Xb), a.out(x), float(xtol), int(maxfev), a.out(info, np.int32),
+                                                   a.out(nfev, np.int32), a.out(njev, np.int32), a.out(fnorm), HOST))
         return dict(x=x, info=info, nfev=nfev, njev=njev, fnorm=fnorm)
 
     def continuation_param_batch(self, shape, mparams, time, Xb, x, step, param_idx, goal, xtol=1e-8,
@@ -354,7 +383,7 @@ class Engine:
         a = _Arg(HOST)
         self._check(self._L.socp_continuation_param_batch(
             self._h, ctypes.byref(shape), B, a.out(mparams), a.inp(time), a.inp(Xb), a.out(x), float(xtol),
-            int(maxfev), float(step), int(param_idx), a.inp(goal), float(step_min), a.out(info), a.out(calls)))
+            int(maxfev), float(step), int(param_idx), a.inp(goal), float(step_min), a.out(info, np.int32), a.out(calls, np.int32)))
         return dict(x=x, info=info, calls=calls, mparams=mparams)
 
     def continuation_boundary_batch(self, shape, mparams, time_prec, Xb_prec, time_des, Xb_des, x, step,
@@ -369,5 +398,5 @@ class Engine:
         self._check(self._L.socp_continuation_boundary_batch(
             self._h, ctypes.byref(shape), B, a.inp(mparams), a.inp(time_prec), a.inp(Xb_prec),
             a.inp(time_des), a.inp(Xb_des), a.out(x), float(xtol), int(maxfev), float(step),
-            float(step_min), a.out(info), a.out(calls)))
+            float(step_min), a.out(info, np.int32), a.out(calls, np.int32)))
         return dict(x=x, info=info, calls=calls)

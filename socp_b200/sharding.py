@@ -17,15 +17,28 @@ def pack_results(x, info, nfev):
     return torch.cat([x, info.to(torch.float64)[:, None], nfev.to(torch.float64)[:, None]], dim=1).contiguous()
 
 
-def gather_results(x, info, nfev, group=None):
-    """All-gather equally sized shards; returns (x[W*B, P], info[W*B], nfev[W*B]) on every rank."""
+def gather_results(x, info, nfev, group=None, total=None):
+    """All-gather the shards; returns (x[T, P], info[T], nfev[T]) on every rank, T = the global problem count.
+
+    Shards may be ragged (shard_bounds gives the last ranks short or empty blocks when `total` is not a
+    multiple of the world size): every rank pads its block to ceil(total/world) rows for the collective and
+    the padding is trimmed afterwards.  total=None means equally sized shards (T = world * rows)."""
     pack = pack_results(x, info, nfev)
     world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rows, width = pack.shape
     if world == 1:
-        out = pack
+        out = pack if total is None else pack[:total]
     else:
-        out = torch.empty((world * pack.shape[0], pack.shape[1]), dtype=pack.dtype, device=pack.device)
+        per = rows if total is None else -(-int(total) // world)
+        if rows > per:
+            raise ValueError("shard of %d rows exceeds ceil(total/world) = %d" % (rows, per))
+        if rows < per:
+            pad = torch.zeros((per - rows, width), dtype=pack.dtype, device=pack.device)
+            pack = torch.cat([pack, pad], dim=0).contiguous()
+        out = torch.empty((world * per, width), dtype=pack.dtype, device=pack.device)
         dist.all_gather_into_tensor(out, pack, group=group)
+        if total is not None:
+            out = out[:int(total)]          # contiguous blocks in rank order: the padding sits at the end
     P = x.shape[1]
     return out[:, :P], out[:, P].to(torch.int32), out[:, P + 1].to(torch.int32)
 

@@ -1,0 +1,59 @@
+"""Host-side logic of bench.py that needs no GPU: the CPU pool keeps the order of its problems, and the
+parity objects report what they say."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def test_cpu_pool_keeps_problem_order(oracle_lib):
+    import bench
+    import scenarios as S
+    from backends import OracleBackend
+    specs = []
+    for k in range(5):
+        s = S.di_problem()
+        s["Xb"][1][1] = 15.0 + k
+        specs.append(s)
+    pool = bench.CpuPool(cores=3)
+    try:
+        _, res = pool.solve(specs)
+    finally:
+        pool.close()
+    ora = OracleBackend()
+    for s, r in zip(specs, res):
+        o = ora.solve(s)
+        assert (r[0], r[1]) == (o["info"], o["nfev"])
+        assert np.linalg.norm(r[2] - o["x"]) <= 1e-8 * np.linalg.norm(o["x"])
+    # the problems differ, so a permutation would show
+    assert len({tuple(np.round(r[2], 6)) for r in res}) == 5
+
+
+def test_parity_solve_counts():
+    import bench
+    x = np.ones((4, 3))
+    ref = [(1, 10, x[0]), (1, 11, x[1] * (1 + 1e-3)), (4, 50, x[2]), (1, 12, x[3])]
+    p = bench.parity_solve(np.array([1, 1, 1, 5]), np.array([10, 11, 40, 12]), x, ref, 1e-6)
+    assert p["sample"] == 4
+    assert p["identical_info"] == 0.5 and p["identical_info_nfev"] == 0.5
+    assert p["both_converged"] == 2 and p["x_within_xtol"] == 0.5
+    assert abs(p["x_rel_err_max"] - 1e-3 / (1 + 1e-3)) < 1e-9
+    assert p["max_abs_nfev_diff"] == 10
+
+
+def test_parity_ensemble_membership():
+    import bench
+    runs = [[(1, 100), (1, 120), (4, 300)], [(1, 90), (1, 90), (1, 90)]]
+    ref = [(1, 100, None), (1, 90, None)]
+    p = bench.parity_ensemble(np.array([4, 1]), np.array([310, 120]), ref, runs)
+    assert p["reference_stable_fraction"] == 0.5
+    assert p["gpu_in_ensemble"] == 0.5 and p["reference_in_ensemble"] == 1.0
+
+
+def test_reference_xstar_is_the_golden_solution():
+    import bench
+    x = bench.reference_xstar()
+    assert x.shape == (85,) and abs(x[84] - 0.21965083876703931) < 1e-15      # tf of Goddard stage 1

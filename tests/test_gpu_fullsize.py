@@ -40,7 +40,6 @@ def test_goddard_batch_1e5_properties(eng, oracle_lib):
     # shooting.cpp:588; SURVEY.md section 8c saw the same in the reference).  The engine reports |F| so
     # that callers can tell the two apart.
     ok = info1 == 1
-    assert 0.3 < ok.mean() < 0.5                                   # the trivial-guess solve is a coin flip
     true_root = ok & (fn1 < 1e-5)
     assert true_root.sum() >= 0.97 * ok.sum(), (true_root.sum(), ok.sum())
     assert set(np.unique(info1)) <= {1, 2, 3, 4, 5}
@@ -53,20 +52,46 @@ def test_goddard_batch_1e5_properties(eng, oracle_lib):
     sub = rng.permutation(B)[:5000]
     xs, infos, nfevs, _ = solve(sub)
     assert np.array_equal(infos, info1[sub]) and np.array_equal(nfevs, nfev1[sub]) and np.array_equal(xs, x1[sub])
-    # a sample against the oracle.  From the trivial costate guess most members are chaotic in the reference
-    # itself (a 2-ulp change of x0 flips info / nfev, tests/test_gpu_solver.py::oracle_ensemble), so paths are
-    # compared statistically: same success rate within sampling error; members that happen to take the
-    # same path must land on the same solution.
-    from backends import OracleBackend
-    ora = OracleBackend()
-    sample = rng.permutation(B)[:64]
-    o_ok = 0
-    for k in sample:
-        o = ora.solve(bench.spec_of(k, mp, time_, Xb, x0))
-        o_ok += (o["info"] == 1)
-        if o["info"] == 1 and info1[k] == 1 and o["nfev"] == nfev1[k]:
-            assert np.linalg.norm(x1[k] - o["x"]) <= 1e-6 * np.linalg.norm(o["x"])
-    assert abs(o_ok / 64.0 - ok.mean()) < 0.2, (o_ok / 64.0, ok.mean())
+    # a sample against the reference.  From the trivial costate guess most members are chaotic in the reference
+    # itself (a rounding-level change of the arithmetic flips info / nfev: its FMA and non-FMA CPU builds agree
+    # on 0 of 32 problems), so paths are compared statistically: the success rate of 512 reference solves and the
+    # GPU's rate over the whole batch must agree within the 3-sigma binomial band of the sample; members that
+    # happen to take the same path must land on the same solution.
+    n_s = 512
+    sample = rng.permutation(B)[:n_s]
+    pool = bench.CpuPool()
+    try:
+        _, res = pool.solve([bench.spec_of(k, mp, time_, Xb, x0) for k in sample])
+    finally:
+        pool.close()
+    o_ok = sum(1 for r in res if r[0] == 1)
+    for k, r in zip(sample, res):
+        if r[0] == 1 and info1[k] == 1 and r[1] == nfev1[k]:
+            assert np.linalg.norm(x1[k] - r[2]) <= 1e-6 * np.linalg.norm(r[2])
+    p_ref, p_gpu = o_ok / float(n_s), float(ok.mean())
+    band = 3.0 * np.sqrt(p_gpu * (1.0 - p_gpu) / n_s)
+    assert abs(p_ref - p_gpu) <= band, (p_ref, p_gpu, band)
+    # the evaluation counts have the same distribution too (medians within 10 %)
+    med_ref, med_gpu = np.median([r[1] for r in res]), np.median(nfev1[sample])
+    assert abs(med_ref - med_gpu) <= 0.1 * med_ref, (med_ref, med_gpu)
+
+
+def test_goddard_warm_batch_1e5_properties(eng, oracle_lib):
+    """The well-conditioned half of the benchmark (bench.py stage2.warm_start) at full size: every member
+    converges to a true root in about P + 6 evaluations, bitwise deterministic."""
+    sys.path.insert(0, ROOT)
+    import bench
+    B = 100000
+    w = bench.wl_goddard_warm(eng, B, seed=20260002)
+    x = np.ascontiguousarray(w.x0).copy()
+    r = eng.solve_batch(w.shape, w.mp, w.time, w.Xb, x, xtol=w.xtol, maxfev=10000)
+    info, nfev, fn = r["info"].copy(), r["nfev"].copy(), r["fnorm"].copy()
+    x1 = r["x"].copy()
+    assert np.all(info == 1) and np.all(fn < 1e-5)
+    assert np.all(nfev >= w.P + 3) and np.all(nfev <= w.P + 12), (nfev.min(), nfev.max())
+    x = np.ascontiguousarray(w.x0).copy()
+    r2 = eng.solve_batch(w.shape, w.mp, w.time, w.Xb, x, xtol=w.xtol, maxfev=10000)
+    assert np.array_equal(r2["info"], info) and np.array_equal(r2["nfev"], nfev) and np.array_equal(r2["x"], x1)
 
 
 def test_rk4_1e6_trajectories(eng, oracle_lib):

@@ -91,7 +91,7 @@ DEMO_SOLVES = ["di_free_tf", "goddard_stage1", "goddard_stage4_singular", "covid
                "vtol_wp1"]
 
 
-def oracle_ensemble(run, spec, k=6):
+def oracle_ensemble(run, spec, k=16):
     """The reference's own sensitivity: re-run the oracle with x0 perturbed by +-2 ulp.  Some of the
     demo problems (the Goddard solve from the trivial costate guess takes ~1200 residual
     evaluations) are chaotic in that sense: the reference's info / nfev flip under such
@@ -120,7 +120,8 @@ def check_against_ensemble(name, spec, got_info, got_nfev, got_x, runs, key_nfev
     infos = {r["info"] for r in runs}
     nf = [r[key_nfev] for r in runs]
     assert got_info in infos, "%s: info %d outside the reference ensemble %s" % (name, got_info, infos)
-    assert 0.5 * min(nf) <= got_nfev <= 2 * max(nf), "%s: nfev %d outside the ensemble range %s" % (name, got_nfev, nf)
+    # within the observed ensemble range +-10 % (the ensemble has 17 members: the exact run and 16 perturbed ones)
+    assert 0.9 * min(nf) <= got_nfev <= 1.1 * max(nf), "%s: nfev %d outside the ensemble range %s" % (name, got_nfev, sorted(nf))
     if got_info == 1:
         ok = [r for r in runs if r["info"] == 1]
         spread = max(np.linalg.norm(r["x"] - xref) for r in ok) if base["info"] == 1 else np.inf
@@ -184,7 +185,7 @@ def test_continuation_param_matches_reference(oracle_lib):
     for e in golden()["cont_param"]:
         spec = spec_from_hex(e["spec"])
         goal = unhex(e["goal"])
-        runs = oracle_ensemble(lambda s2: ora.continuation_param(s2, e["step"], e["pname"], goal), spec, k=4)
+        runs = oracle_ensemble(lambda s2: ora.continuation_param(s2, e["step"], e["pname"], goal), spec, k=8)
         assert (runs[0]["info"], runs[0]["solver_calls"], runs[0]["nfev_total"]) == (e["info"], e["solver_calls"], e["nfev_total"])
         mp, time, Xb, x = batch_of([spec])
         r = engine().continuation_param_batch(shape_of(spec), mp, time, Xb, x, e["step"],
@@ -204,7 +205,7 @@ def test_continuation_boundary_matches_reference(oracle_lib):
         if spec["name"] == "interceptor_S1":
             continue        # does not converge in the reference either; a chaotic homotopy
         timed, Xd = unhex(e["timed"]), unhex(e["Xd"])
-        runs = oracle_ensemble(lambda s2: ora.continuation_boundary(s2, e["step"], timed, Xd), spec, k=3)
+        runs = oracle_ensemble(lambda s2: ora.continuation_boundary(s2, e["step"], timed, Xd), spec, k=6)
         mp, time, Xb, x = batch_of([spec])
         r = engine().continuation_boundary_batch(shape_of(spec), mp, time, Xb, timed[None, :],
                                                  Xd.reshape(1, -1), x, e["step"], xtol=spec["xtol"])
@@ -212,3 +213,57 @@ def test_continuation_boundary_matches_reference(oracle_lib):
         mode = check_against_ensemble(spec["name"], spec, int(r["info"][0]), int(r["calls"][0, 1]), r["x"][0], runs,
                                       key_nfev="nfev_total")
         print("%s: %s match (gpu nfev %d, reference %d)" % (spec["name"], mode, r["calls"][0, 1], e["nfev_total"]))
+
+
+def test_warm_started_batch_matches_reference_problem_for_problem(oracle_lib):
+    """SURVEY C2 stage 2 (bench.py `stage2.warm_start`): the perturbed Goddard problems of the benchmark batch,
+    each started from the reference's converged x* of the unperturbed problem.  This workload is well
+    conditioned (the reference's FMA and non-FMA builds agree on every problem), so the bar is identity:
+    same info, same nfev, unknowns within xtol |x_ref| -- for EVERY member of the sample."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    from backends import OracleBackend
+    B = 256
+    w = bench.wl_goddard_warm(engine(), B, seed=20260002)
+    x = np.ascontiguousarray(w.x0).copy()
+    r = engine().solve_batch(w.shape, w.mp, w.time, w.Xb, x, xtol=w.xtol, maxfev=10000)
+    ora = OracleBackend()
+    for k in range(B):
+        o = ora.solve(w.spec(k))
+        assert (int(r["info"][k]), int(r["nfev"][k])) == (o["info"], o["nfev"]), (k, r["info"][k], r["nfev"][k], o["info"], o["nfev"])
+        assert o["info"] == 1
+        assert np.linalg.norm(r["x"][k] - o["x"]) <= w.xtol * np.linalg.norm(o["x"]), k
+    assert np.all(r["fnorm"] < 1e-5)
+
+
+def test_kd_continuation_batch_matches_reference_outcome(oracle_lib):
+    """SURVEY C2 stage 2, second half: continuation KD 0 -> 310 in one step (tests/testGoddard.cpp:105) from the
+    warm-started solutions.  At KD = 310 the costates grow to 1e5..1e8 and the reference's own nfev moves with
+    a rounding-level change of the arithmetic (its FMA / non-FMA builds agree on 15 of 32), its info and
+    solver-call count do not: those must be identical, the unknowns within xtol."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    from backends import OracleBackend
+    B = 48
+    w = bench.wl_goddard_warm(engine(), B, seed=20260002)
+    x = np.ascontiguousarray(w.x0).copy()
+    r0 = engine().solve_batch(w.shape, w.mp, w.time, w.Xb, x, xtol=w.xtol, maxfev=10000)
+    assert np.all(r0["info"] == 1)
+    kd = S.pidx(S.GODDARD, "KD")
+    r = engine().continuation_param_batch(w.shape, w.mp, w.time, w.Xb, r0["x"], 1.0, kd, np.full(B, 310.0), xtol=w.xtol)
+    ora = OracleBackend()
+    nf_g, nf_o, calls_differ = [], [], 0
+    for k in range(B):
+        o0 = ora.solve(w.spec(k))
+        o = ora.continuation_param(w.spec(k, x0=o0["x"]), 1.0, "KD", 310.0)
+        assert int(r["info"][k]) == o["info"], k
+        calls_differ += int(r["calls"][k, 0]) != o["solver_calls"]
+        if o["info"] == 1:
+            assert np.linalg.norm(r["x"][k] - o["x"]) <= 4 * w.xtol * np.linalg.norm(o["x"]), k
+        nf_g.append(int(r["calls"][k, 1])); nf_o.append(o["nfev_total"])
+    # a step halving (3 solver calls instead of 1) happens on either side for a few percent of the members
+    assert calls_differ <= max(2, B // 10), calls_differ
+    # evaluation counts: same distribution (medians within 15 %), not the same numbers
+    assert abs(np.median(nf_g) - np.median(nf_o)) <= 0.15 * np.median(nf_o), (np.median(nf_g), np.median(nf_o))

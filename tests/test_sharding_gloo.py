@@ -30,7 +30,7 @@ def _worker(rank, world, port, total, outdir):
     from backends import OracleBackend
     ora = OracleBackend()
     lo, hi = sharding.shard_bounds(total, rank, world)
-    assert hi - lo == total // world
+    assert hi - lo == max(0, min(-(-total // world), total - rank * -(-total // world)))
     # each rank solves its own block of double-integrator problems with different targets
     xs, infos, nfevs = [], [], []
     for k in range(lo, hi):
@@ -38,8 +38,8 @@ def _worker(rank, world, port, total, outdir):
         spec["Xb"][1][1] = 15.0 + k
         r = ora.solve(spec)
         xs.append(r["x"]); infos.append(r["info"]); nfevs.append(r["nfev"])
-    x = torch.tensor(np.array(xs)); info = torch.tensor(infos, dtype=torch.int32); nfev = torch.tensor(nfevs, dtype=torch.int32)
-    gx, gi, gn = sharding.gather_results(x, info, nfev)
+    x = torch.tensor(np.array(xs).reshape(-1, 13)); info = torch.tensor(infos, dtype=torch.int32); nfev = torch.tensor(nfevs, dtype=torch.int32)
+    gx, gi, gn = sharding.gather_results(x, info, nfev, total=total)
     tot = sharding.reduce_sum([float((info == 1).sum()), float(nfev.sum())], "cpu")
     tmax = sharding.reduce_max(float(rank + 1), "cpu")
     assert tmax == world
@@ -51,10 +51,10 @@ def _worker(rank, world, port, total, outdir):
     dist.destroy_process_group()
 
 
-def test_two_rank_shard_and_gather(tmp_path, oracle_lib):
+@pytest.mark.parametrize("total,world", [(6, 2), (5, 2), (1, 2)])     # equal, ragged and empty last shard
+def test_two_rank_shard_and_gather(tmp_path, oracle_lib, total, world):
     import scenarios as S
     from backends import OracleBackend
-    total, world = 6, 2
     mp.spawn(_worker, args=(world, _free_port(), total, str(tmp_path)), nprocs=world, join=True)
     gx = np.load(tmp_path / "gx.npy")
     gi = np.load(tmp_path / "gi.npy")
