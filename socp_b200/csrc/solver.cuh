@@ -32,13 +32,16 @@ namespace socp {
 enum { PH_IDLE = 0, PH_F0 = 1, PH_JAC = 2, PH_TRIAL = 3 };
 enum { RUN_SOLVE = 0, RUN_RESIDUAL = 1, RUN_FDJAC = 2 };
 // per-problem integer state
-enum { I_PHASE = 0, I_ITER, I_NCSUC, I_NCFAIL, I_NSLOW1, I_NSLOW2, I_JEVAL, I_NFEV, I_INFO, I_BASE, I_NJEV, I_COUNT = 12 };
+// I_PEND: the rotations of the last Broyden update (scr) have not been applied to Q yet (split build)
+enum { I_PHASE = 0, I_ITER, I_NCSUC, I_NCFAIL, I_NSLOW1, I_NSLOW2, I_JEVAL, I_NFEV, I_INFO, I_BASE, I_NJEV, I_PEND, I_COUNT = 12 };
 // per-problem scalar state
 enum { D_DELTA = 0, D_XNORM, D_FNORM, D_PNORM, D_COUNT = 4 };
 
 struct SolverDev {
     // shape
     int model_id, dim, N, M, S, P, nfree, np, nJ, REC, LR;
+    int QS;                                // doubles between the Q / fjac matrices of two problems: P*P rounded up to an
+                                           // even count, so that every matrix starts 16-byte aligned (bulk copies)
     int mode_t[SOCP_MAX_NODES];
     int mode_X[SOCP_MAX_NODES][SOCP_MAX_DIM];
     const int *jac_col, *jac_seg;          // [nJ] work item -> (column, segment)
@@ -410,7 +413,7 @@ __global__ void __launch_bounds__(256) zero_fjac_kernel(SolverDev D, int cur) {
     const int *jac_list = D.lists + (size_t)(cur * 2 + 1) * D.B;
     const long pp = (long)D.P * D.P;
     for (long w = (long)blockIdx.x * blockDim.x + threadIdx.x; w < (long)njac * pp; w += (long)gridDim.x * blockDim.x)
-        D.fjac[(size_t)jac_list[w / pp] * pp + (w % pp)] = 0.;
+        D.fjac[(size_t)jac_list[w / pp] * D.QS + (w % pp)] = 0.;
 }
 
 // ---- kernel 2a: assemble residuals and forward-difference Jacobian columns ----------------------
@@ -440,7 +443,7 @@ assemble_kernel(SolverDev D, int cur) {
             const int *is = D.istate + b * I_COUNT;
             const double *be = D.ends + ((b * 2 + is[I_BASE]) * D.M) * D.REC;
             const double h = fd_step(D.xe[b * n + j], D.epsfcn);
-            double *colj = D.fjac + (size_t)b * n * n + (size_t)j * n;
+            double *colj = D.fjac + (size_t)b * D.QS + (size_t)j * n;
             const double *fvec = D.fvec + b * n;
             // an unknown of node s enters segment s - 1 (as the right-hand state of its continuity rows) and
             // segment s (as its start point); a free time moves every segment
@@ -594,7 +597,7 @@ assemble_jac_kernel(SolverDev D, int cur) {
         const long b = jac_list[w];
         const double *xe = D.xe + b * P;
         const double *mp = D.mparams + b * M::NP;
-        double *J = D.fjac + (size_t)b * P * P;
+        double *J = D.fjac + (size_t)b * D.QS;
         auto put = [&](int row, int col, double v) { J[row + (size_t)col * P] = v; };     // dF_row / dx_col
         for (int e = 0; e < P * P; ++e) J[e] = 0.;
         double tl[SOCP_MAX_NODES + 1], sw[2] = {0.0227, 0.08};
@@ -1233,6 +1236,17 @@ __device__ void r1coef_g(int n, const double *v, const double *w, double *scr) {
     gsync<G>();
 }
 
+// One step of r1mpyq on the pair (a_j, a_n).  Explicit roundings (no contraction left to the compiler): the
+// fused Broyden kernel and the split Q pass must produce the same bits from the same rotations.
+SOCP_DEV void rot_first(double c, double s, double aj, double &an, double &out) {      // first set, j = n-2 .. 0
+    out = __fma_rn(c, aj, -__dmul_rn(s, an));
+    an = __fma_rn(s, aj, __dmul_rn(c, an));
+}
+SOCP_DEV void rot_second(double c, double s, double aj, double &an, double &out) {     // second set, j = 0 .. n-2
+    out = __fma_rn(c, aj, __dmul_rn(s, an));
+    an = __fma_rn(-s, aj, __dmul_rn(c, an));
+}
+
 // r1mpyq: apply the recorded rotations to A (m x n, column-major, lda): one thread per row, the
 // row streamed through registers in chunks of 8 columns so that the loads overlap the chain.
 // `extra` (length n, stride 1) is transformed as one more row (r1mpyq(1, n, qtf, 1, ...) of hybrd).
@@ -1251,12 +1265,7 @@ __device__ void r1mpyq_g(int m, int n, double *a, int lda_a, const double *scr, 
 #pragma unroll
             for (int k = 0; k < CH; ++k) if (j0 - k >= 0) buf[k] = row[(size_t)(j0 - k) * lda];
 #pragma unroll
-            for (int k = 0; k < CH; ++k) if (j0 - k >= 0) {
-                const int j = j0 - k;
-                const double aj = buf[k];
-                buf[k] = c1[j] * aj - s1[j] * an;
-                an = s1[j] * aj + c1[j] * an;
-            }
+            for (int k = 0; k < CH; ++k) if (j0 - k >= 0) rot_first(c1[j0 - k], s1[j0 - k], buf[k], an, buf[k]);
 #pragma unroll
             for (int k = 0; k < CH; ++k) if (j0 - k >= 0) row[(size_t)(j0 - k) * lda] = buf[k];
         }
@@ -1264,18 +1273,127 @@ __device__ void r1mpyq_g(int m, int n, double *a, int lda_a, const double *scr, 
 #pragma unroll
             for (int k = 0; k < CH; ++k) if (j0 + k < n - 1) buf[k] = row[(size_t)(j0 + k) * lda];
 #pragma unroll
-            for (int k = 0; k < CH; ++k) if (j0 + k < n - 1) {
-                const int j = j0 + k;
-                const double aj = buf[k];
-                buf[k] = c2[j] * aj + s2[j] * an;
-                an = -s2[j] * aj + c2[j] * an;
-            }
+            for (int k = 0; k < CH; ++k) if (j0 + k < n - 1) rot_second(c2[j0 + k], s2[j0 + k], buf[k], an, buf[k]);
 #pragma unroll
             for (int k = 0; k < CH; ++k) if (j0 + k < n - 1) row[(size_t)(j0 + k) * lda] = buf[k];
         }
         row[(size_t)(n - 1) * lda] = an;
     }
     gsync<G>();
+}
+
+// ---- bulk copies (TMA engine, non-tensor form) and their mbarrier -----------------------------------------
+SOCP_DEV unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+SOCP_DEV void mbar_init(unsigned long long *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+SOCP_DEV void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+SOCP_DEV bool mbar_try_wait(unsigned long long *bar, unsigned parity) {
+    unsigned ok;
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// global -> shared, completion counted in bytes on the mbarrier; 16-byte aligned addresses, size % 16 == 0
+SOCP_DEV void bulk_g2s(void *smem_dst, const void *gmem_src, unsigned bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// shared -> global as one bulk group; bulk_wait_read() returns when the shared source may be overwritten
+SOCP_DEV void bulk_s2g(void *gmem_dst, const void *smem_src, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+SOCP_DEV void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+SOCP_DEV void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// order this thread's generic-proxy accesses to shared memory before later async-proxy (bulk copy) accesses
+SOCP_DEV void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---- kernel 2b-1 (split build): one streaming pass over Q per Broyden iteration ---------------------------
+// For every problem whose trial residual arrived: bring Q (P x P, column major) into shared memory with ONE
+// bulk copy, apply the 2(P-1) Givens rotations the previous Broyden update recorded but did not apply
+// (MINPACK r1mpyq, deferred by one iteration: I_PEND), write Q back with one bulk copy, and form
+// sum = Q^T F(x + p) from the copy in shared memory.  Q is read once and written once per iteration
+// (the fused kernel read it twice: once for Q^T f, once for r1mpyq) and nothing here is a cross-thread
+// dependent chain: one thread per row for the rotations, one warp per column for the dot products.
+// The chain kernel (hybrd_res_kernel, SPLIT) consumes `sum` (D.wa2) and records the next rotations (D.scr).
+__global__ void __launch_bounds__(128)
+hybrd_qpass_kernel(SolverDev D, int cur) {
+    extern __shared__ __align__(128) double qp_smem[];
+    const int n = D.P, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NT = 128, NW = 4;
+    double *Qs = qp_smem;                               // [QS]
+    double *wv = Qs + D.QS;                             // [n]  F(x + p)
+    double *cf = wv + ((n + 1) & ~1);                   // [4n] c1 s1 c2 s2 (r1coef layout)
+    unsigned long long *bar = (unsigned long long *)(cf + 4 * n);
+    const int nres = D.counts[cur * 2 + 0];
+    const int *res_list = D.lists + (size_t)(cur * 2 + 0) * D.B;
+    const unsigned qbytes = (unsigned)D.QS * 8u;
+    if (tid == 0) mbar_init(bar, 1);
+    __syncthreads();
+    unsigned parity = 0;
+    for (long g = blockIdx.x; g < nres; g += gridDim.x) {
+        const long b = res_list[g];
+        int *is = D.istate + b * I_COUNT;
+        if (is[I_PHASE] != PH_TRIAL) continue;          // first residual of a solve: nothing to do (uniform)
+        const int pend = is[I_PEND];
+        double *Qg = D.fjac + (size_t)b * D.QS;
+        if (tid == 0) {
+            mbar_expect_tx(bar, qbytes);
+            bulk_g2s(Qs, Qg, qbytes, bar);
+        }
+        for (int i = tid; i < n; i += NT) wv[i] = D.wa4[b * n + i];
+        if (pend) for (int i = tid; i < 4 * n; i += NT) cf[i] = D.scr[b * 4 * (size_t)n + i];
+        __syncthreads();
+        while (!mbar_try_wait(bar, parity)) {}
+        parity ^= 1u;
+        if (pend) {
+            const double *c1 = cf, *s1 = cf + n, *c2 = cf + 2 * n, *s2 = cf + 3 * n;
+            for (int i = tid; i < n; i += NT) {         // one thread per row; consecutive threads, consecutive words
+                double *row = Qs + i;
+                double an = row[(size_t)(n - 1) * n];
+                for (int j = n - 2; j >= 0; --j) { double o; rot_first(c1[j], s1[j], row[(size_t)j * n], an, o); row[(size_t)j * n] = o; }
+                for (int j = 0; j < n - 1; ++j) { double o; rot_second(c2[j], s2[j], row[(size_t)j * n], an, o); row[(size_t)j * n] = o; }
+                row[(size_t)(n - 1) * n] = an;
+            }
+            fence_async_smem();
+            __syncthreads();
+            if (tid == 0) bulk_s2g(Qg, Qs, qbytes);
+        }
+        // sum_j = Q(:, j) . F(x + p): one warp per column, four columns in flight; per lane the rows
+        // lane, lane + 32, lane + 64 of a 96-row block accumulate in that order, then the xor butterfly
+        // 16, 8, 4, 2, 1 (the summation tree of the fused kernel: the two builds agree bit for bit)
+        for (int j0 = 4 * warp; j0 < n; j0 += 4 * NW) {
+            double p0 = 0., p1 = 0., p2 = 0., p3 = 0.;
+            for (int i0 = 0; i0 < n; i0 += 96) {
+#pragma unroll
+                for (int u = 0; u < 3; ++u) {
+                    const int i = i0 + 32 * u + lane;
+                    const double wi = (i < n) ? wv[i] : 0.;
+                    const double q0 = (i < n) ? Qs[(size_t)j0 * n + i] : 0.;
+                    const double q1 = (i < n && j0 + 1 < n) ? Qs[(size_t)(j0 + 1) * n + i] : 0.;
+                    const double q2 = (i < n && j0 + 2 < n) ? Qs[(size_t)(j0 + 2) * n + i] : 0.;
+                    const double q3 = (i < n && j0 + 3 < n) ? Qs[(size_t)(j0 + 3) * n + i] : 0.;
+                    p0 = fma(q0, wi, p0); p1 = fma(q1, wi, p1); p2 = fma(q2, wi, p2); p3 = fma(q3, wi, p3);
+                }
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                p0 += __shfl_xor_sync(0xffffffffu, p0, off); p1 += __shfl_xor_sync(0xffffffffu, p1, off);
+                p2 += __shfl_xor_sync(0xffffffffu, p2, off); p3 += __shfl_xor_sync(0xffffffffu, p3, off);
+            }
+            if (lane < 4 && j0 + lane < n) D.wa2[b * n + j0 + lane] = (lane == 0) ? p0 : (lane == 1) ? p1 : (lane == 2) ? p2 : p3;
+        }
+        if (tid == 0) {
+            if (pend) { is[I_PEND] = 0; bulk_wait_read(); }     // the copy out has read the shared buffer
+        }
+        fence_async_smem();
+        __syncthreads();                                        // buffer free for the next problem's bulk load
+    }
+    if (tid == 0) bulk_wait_all();
 }
 
 // ---- shared state of one problem inside the Powell-hybrid kernels ------------------------------
@@ -1366,7 +1484,7 @@ hybrd_res_kernel(SolverDev D, int cur, int per_group_doubles) {
         W.x = vec; W.xe = vec + n; W.fvec = vec + 2 * n; W.diag = vec + 3 * n; W.qtf = vec + 4 * n;
         W.wa1 = vec + 5 * n; W.wa4 = vec + 6 * n; W.wa2 = vec + 7 * n; W.wa3 = vec + 8 * n; W.scr = vec + 9 * n;
         W.r = STAGE_R ? vec + 13 * n : D.r + (size_t)b * D.LR;
-        W.q = D.fjac + (size_t)b * n * n;
+        W.q = D.fjac + (size_t)b * D.QS;
         W.ldq = n;
         l2_prefetch<G>(W.q, (size_t)n * n * sizeof(double));      // Q is first touched ~20 us from now
         gcopy_async<G>(W.x, D.x + b * n, n); gcopy_async<G>(W.xe, D.xe + b * n, n); gcopy_async<G>(W.fvec, D.fvec + b * n, n);
@@ -1567,7 +1685,7 @@ hybrd_jac_kernel(SolverDev D, int cur, int per_group_doubles) {
         double *after = vec + 13 * n;
         W.r = STAGE_R ? after : D.r + (size_t)b * D.LR;
         if (STAGE_R) after += D.LR;
-        double *gq = D.fjac + (size_t)b * n * n;
+        double *gq = D.fjac + (size_t)b * D.QS;
         W.q = STAGE_Q ? after : gq;
         W.ldq = STAGE_Q ? ldq_s : n;
         long long phase_t0 = clock64();
@@ -1649,7 +1767,10 @@ __global__ void solver_finish(SolverDev D, long first, double *x_out, double *fv
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (x_out && i < D.B * D.P) x_out[first * D.P + i] = D.x[i];
     if (fvec_out && i < D.B * D.P) fvec_out[first * D.P + i] = D.fvec[i];
-    if (fjac_out && i < D.B * (long)D.P * D.P) fjac_out[first * (long)D.P * D.P + i] = D.fjac[i];
+    if (fjac_out && i < D.B * (long)D.P * D.P) {
+        const long pp = (long)D.P * D.P;
+        fjac_out[first * pp + i] = D.fjac[(i / pp) * D.QS + (i % pp)];
+    }
     if (i < D.B) {
         const int *is = D.istate + i * I_COUNT;
         // a problem still in flight when the round limit is hit is NOT a hybrd outcome: it gets its own code
