@@ -1435,12 +1435,12 @@ SOCP_DEV double *group_smem(const SolverDev &D, int per_group_doubles) {
 }
 
 // ---- kernel 2b: problems whose residual arrived (first evaluation or trial point) ---------------
-// 4 CTAs/SM: after the instruction-level pass the kernel fits 128 registers without spills and the fourth
-// co-resident problem is worth -12 % kernel time (before it, the 128-register build spilled and 3 CTAs/SM
-// at 167 registers measured the same; 5 CTAs/SM were worse -- DESIGN.md section 5)
-template <int G, bool STAGE_R>
-__global__ void __launch_bounds__(128, 4)
-hybrd_res_kernel(SolverDev D, int cur, int per_group_doubles) {
+// SPLIT = false: the fused kernel (one group does everything of a Broyden iteration, Q swept twice from
+// global memory).  SPLIT = true: the chain kernel of the split build -- Q never appears here: sum = Q^T F(x + p)
+// was left in D.wa2 by hybrd_qpass_kernel, the 2(P-1) rotations of this update go to D.scr for the next Q pass
+// (I_PEND) and only qtf is rotated on the spot.
+template <int G, bool STAGE_R, bool SPLIT>
+SOCP_DEV void res_loop(const SolverDev &D, int cur, int per_group_doubles) {
     const int GROUPS = (G == 32) ? (int)(blockDim.x >> 5) : 1;
     const int grp = (G == 32) ? (threadIdx.x >> 5) : 0;
     const int tid = threadIdx.x % G;
@@ -1486,7 +1486,7 @@ hybrd_res_kernel(SolverDev D, int cur, int per_group_doubles) {
         W.r = STAGE_R ? vec + 13 * n : D.r + (size_t)b * D.LR;
         W.q = D.fjac + (size_t)b * D.QS;
         W.ldq = n;
-        l2_prefetch<G>(W.q, (size_t)n * n * sizeof(double));      // Q is first touched ~20 us from now
+        if (!SPLIT) l2_prefetch<G>(W.q, (size_t)n * n * sizeof(double));      // Q is first touched ~20 us from now
         gcopy_async<G>(W.x, D.x + b * n, n); gcopy_async<G>(W.xe, D.xe + b * n, n); gcopy_async<G>(W.fvec, D.fvec + b * n, n);
         gcopy_async<G>(W.diag, D.diag + b * n, n); gcopy_async<G>(W.qtf, D.qtf + b * n, n); gcopy_async<G>(W.wa1, D.wa1 + b * n, n);
         gcopy_async<G>(W.wa4, D.wa4 + b * n, n);
@@ -1567,7 +1567,7 @@ hybrd_res_kernel(SolverDev D, int cur, int per_group_doubles) {
             // rank-one (Broyden) update of the QR factors: sum_j = Q(:,j) . wa4, one warp per
             // column, four columns in flight so that the HBM/L2 loads of Q overlap
             SOCP_PHASE(16, 2);
-            {
+            if (!SPLIT) {
                 const int lane = threadIdx.x & 31, warp = tid >> 5;
                 constexpr int NW = G / 32, NC = 8;
                 const bool clk_on = D.phase_clocks; unsigned long long *clk_counters = D.counters; long long sub_t0 = clock64();
@@ -1630,6 +1630,15 @@ hybrd_res_kernel(SolverDev D, int cur, int per_group_doubles) {
                     }
                     SOCP_SUB(1);
                 }
+            } else {
+                // split build: sum = Q^T F(x + p) comes from the Q pass (same summation tree, same bits)
+                const double *sumv = D.wa2 + b * n;
+                for (int j = tid; j < n; j += G) {
+                    const double sum = sumv[j];
+                    W.wa2[j] = (sum - W.wa3[j]) / pnorm;
+                    W.wa1[j] = W.diag[j] * ((W.diag[j] * W.wa1[j]) / pnorm);
+                    if (ratio >= p0001) W.qtf[j] = sum;
+                }
             }
             if (tid == 0) atomicAdd(D.counters + 1, 1ULL);
             gsync<G>();
@@ -1637,7 +1646,12 @@ hybrd_res_kernel(SolverDev D, int cur, int per_group_doubles) {
             r1updt_g<G>(n, W.r, W.wa1, W.wa2, W.wa3, W.scr, W.scr + n, W.scr + 2 * n, seq_warp<G>(D.sm_count), D.phase_clocks, D.counters);
             SOCP_PHASE(16, 4);
             r1coef_g<G>(n, W.wa2, W.wa3, W.scr);
-            r1mpyq_g<G>(n, n, W.q, W.ldq, W.scr, W.qtf);
+            if (SPLIT) {
+                // qtf is needed by the dogleg right away: rotate it here (one row); Q waits for the next Q pass
+                r1mpyq_g<G>(0, n, W.q, W.ldq, W.scr, W.qtf);
+                gcopy<G>(D.scr + (size_t)b * 4 * n, W.scr, 4 * n);
+                if (tid == 0) is[I_PEND] = 1;
+            } else r1mpyq_g<G>(n, n, W.q, W.ldq, W.scr, W.qtf);
             SOCP_PHASE(16, 5);
             if (tid == 0) is[I_JEVAL] = 0;
             dogleg_and_request<G>(D, b, W, is, ds, red, next_res, next_cnt);
@@ -1651,6 +1665,25 @@ hybrd_res_kernel(SolverDev D, int cur, int per_group_doubles) {
         gsync<G>();
         SOCP_PHASE(16, 7);
     }
+}
+
+// 4 CTAs/SM: after the instruction-level pass the kernel fits 128 registers without spills and the fourth
+// co-resident problem is worth -12 % kernel time (before it, the 128-register build spilled and 3 CTAs/SM
+// at 167 registers measured the same; 5 CTAs/SM were worse -- DESIGN.md section 5)
+template <int G, bool STAGE_R>
+__global__ void __launch_bounds__(128, 4)
+hybrd_res_kernel(SolverDev D, int cur, int per_group_doubles) {
+    res_loop<G, STAGE_R, false>(D, cur, per_group_doubles);
+}
+
+// The chain kernel of the split build: ONE WARP per problem (no CTA barrier anywhere: every wait is a
+// __syncwarp), as many problems per SM as shared memory holds (R + 13 work vectors per problem).  What is left
+// of a Broyden iteration once Q is gone are the dependent chains (Givens sweeps, back substitution, norms);
+// their latency is hidden by the other warps of the SM instead of by idle threads of the same CTA.
+template <bool STAGE_R>
+__global__ void __launch_bounds__(128, STAGE_R ? 1 : 4)
+hybrd_chain_kernel(SolverDev D, int cur, int per_group_doubles) {
+    res_loop<32, STAGE_R, true>(D, cur, per_group_doubles);
 }
 
 // ---- kernel 2c: problems whose forward-difference Jacobian arrived ------------------------------
@@ -1700,6 +1733,7 @@ hybrd_jac_kernel(SolverDev D, int cur, int per_group_doubles) {
             if (D.analytic) is[I_NJEV] += 1;               // hybrj counts Jacobian calls apart (njev)
             else is[I_NFEV] += n;                          // hybrd: fdjac1 costs n residual evaluations
             is[I_JEVAL] = 1;
+            is[I_PEND] = 0;                                // Q is rebuilt from scratch: nothing pending
             atomicAdd(D.counters + 2, 1ULL);
         }
         for (int i = tid; i < n; i += G) W.qtf[i] = W.fvec[i];

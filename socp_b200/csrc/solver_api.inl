@@ -38,6 +38,7 @@ int make_plan(socp_ctx *ctx, const socp_shape *shape, HostPlan &pl) {
     D.np = kNP[D.model_id];
     D.REC = D.N + 2;
     D.LR = P * (P + 1) / 2;
+    D.QS = (P * P + 1) & ~1;
     D.nfree = P - D.N * D.M;
     D.ode_tol = (shape->integrator == SOCP_DOPRI5) ? shape->ode_tol : 0.;
     if (shape->integrator != SOCP_RK4 && shape->integrator != SOCP_DOPRI5) return fail(ctx, SOCP_ERR_ARG, "bad shape.integrator");
@@ -67,7 +68,7 @@ int make_plan(socp_ctx *ctx, const socp_shape *shape, HostPlan &pl) {
     D.nJ = (int)pl.jac_col.size();
     pl.table_ints = 2 * (size_t)D.nJ + 2 * (size_t)P;
     // persistent bytes per problem
-    size_t dbl = (size_t)P * 10 + 4 * (size_t)P + (size_t)P * P + D.LR + (size_t)(2 * D.M + D.nJ) * D.REC + D_COUNT;
+    size_t dbl = (size_t)P * 10 + 4 * (size_t)P + (size_t)D.QS + D.LR + (size_t)(2 * D.M + D.nJ) * D.REC + D_COUNT;
     pl.bytes_per_problem = dbl * sizeof(double) + (I_COUNT + 4) * sizeof(int) + 2048 / 64;
     return SOCP_OK;
 }
@@ -86,7 +87,7 @@ size_t carve(HostPlan &pl, void *blob, long Bw) {
     D.diag = c.take<double>(Bw * P); D.qtf = c.take<double>(Bw * P);
     D.wa1 = c.take<double>(Bw * P); D.wa2 = c.take<double>(Bw * P); D.wa3 = c.take<double>(Bw * P);
     D.wa4 = c.take<double>(Bw * P); D.scr = c.take<double>(Bw * 4 * P);
-    D.fjac = c.take<double>(Bw * P * P);
+    D.fjac = c.take<double>(Bw * (size_t)D.QS);
     D.r = c.take<double>(Bw * (size_t)D.LR);
     D.ends = c.take<double>(Bw * 2 * (size_t)D.M * D.REC);
     D.jends = c.take<double>(Bw * (size_t)D.nJ * D.REC);
@@ -98,7 +99,7 @@ size_t carve(HostPlan &pl, void *blob, long Bw) {
 }
 
 const int kProfSlots = 16;      // rounds between two harvests of the profiling events
-const int kProfEv = 5;          // events per profiled round
+const int kProfEv = 6;          // events per profiled round: start, integrate, assemble, Q pass, Broyden, Jacobian
 
 cudaEvent_t prof_event(socp_ctx *ctx, int idx) {
     while ((int)ctx->prof_events.size() <= idx) {
@@ -112,16 +113,19 @@ cudaEvent_t prof_event(socp_ctx *ctx, int idx) {
 // accumulate the per-kernel times of the last `n` profiled rounds (events must have completed)
 void prof_harvest(socp_ctx *ctx, int n, FILE *log = nullptr, long round0 = 0, const int *counts = nullptr) {
     for (int k = 0; k < n; ++k) {
-        float a = 0, b = 0, c = 0, d = 0;
-        cudaEventElapsedTime(&a, ctx->prof_events[kProfEv * k], ctx->prof_events[kProfEv * k + 1]);
-        cudaEventElapsedTime(&b, ctx->prof_events[kProfEv * k + 1], ctx->prof_events[kProfEv * k + 2]);
-        cudaEventElapsedTime(&c, ctx->prof_events[kProfEv * k + 2], ctx->prof_events[kProfEv * k + 3]);
+        float a = 0, b = 0, q = 0, c = 0, d = 0;
+        cudaEvent_t *e = &ctx->prof_events[kProfEv * k];
+        cudaEventElapsedTime(&a, e[0], e[1]);          // integrate_worklist (+ variational kernels)
+        cudaEventElapsedTime(&b, e[1], e[2]);          // zero_fjac + assemble
+        cudaEventElapsedTime(&q, e[2], e[3]);          // Q pass (split build; ~0 otherwise)
+        cudaEventElapsedTime(&c, e[2], e[4]);          // Broyden phase: Q pass + chain kernel, or the fused kernel
+        cudaEventElapsedTime(&d, e[4], e[5]);          // Jacobian phase
         ctx->integrate_ms += a; ctx->integrate_launches += 1;
         ctx->assemble_ms += b;
-        cudaEventElapsedTime(&d, ctx->prof_events[kProfEv * k + 3], ctx->prof_events[kProfEv * k + 4]);
+        ctx->qpass_ms += q;
         ctx->advance_ms += c + d; ctx->advance_launches += 2;
         ctx->jac_ms += d;
-        if (log) fprintf(log, "%ld %d %d %.4f %.4f %.4f %.4f\n", round0 + k, counts ? counts[0] : -1, counts ? counts[1] : -1, a, b, c, d);
+        if (log) fprintf(log, "%ld %d %d %.4f %.4f %.4f %.4f %.4f\n", round0 + k, counts ? counts[0] : -1, counts ? counts[1] : -1, a, b, q, c - q, d);
     }
 }
 
@@ -133,6 +137,11 @@ struct SmemPlan {
     bool jac_r_global;                   // Jacobian phase: leave R in global memory when that fits one more CTA per SM
     int doubles_res, doubles_jac;        // shared doubles per group
     size_t bytes_res, bytes_jac;         // per CTA
+    // split Broyden phase (hybrd_qpass_kernel + hybrd_chain_kernel): Q fits one CTA's shared memory
+    bool split;
+    size_t bytes_qpass;                  // per CTA of the Q pass
+    int chain_doubles;                   // per problem (= per warp) of the chain kernel
+    int qpass_per_sm, chain_per_sm;      // resident CTAs / warps per SM
 };
 
 // One warp per problem up to P = 32, a 128-thread CTA above (measured at P = 85: one warp per problem
@@ -164,6 +173,15 @@ SmemPlan smem_plan(const SolverDev &D) {
     const size_t sm_bytes = 227 * 1024;
     p.jac_r_global = p.G == 128 && p.stage_q_jac &&
                      sm_bytes / ((dj - D.LR) * 8 + 1024) > sm_bytes / (dj * 8 + 1024);
+    // Split Broyden phase for 32 < P: the Q pass stages the whole Q (QS doubles) + F(x+p) + 4 P coefficients
+    // + the mbarrier in one CTA; the chain kernel needs R + 13 vectors per warp.  SOCP_BROYDEN=fused keeps the
+    // one-kernel form (A/B measurements, and the fallback when Q does not fit: P > ~165).
+    p.bytes_qpass = ((size_t)D.QS + ((D.P + 1) & ~1) + 4 * (size_t)D.P + 2) * 8;
+    p.chain_doubles = (int)dr;
+    const char *mode = getenv("SOCP_BROYDEN");
+    p.split = p.G == 128 && p.stage_r && p.bytes_qpass <= limit && !(mode && !strcmp(mode, "fused"));
+    p.qpass_per_sm = (int)std::max<size_t>(1, sm_bytes / (p.bytes_qpass + 1024));
+    p.chain_per_sm = (int)std::min<size_t>(16, std::max<size_t>(1, sm_bytes / (dr * 8 + 1024)));
     return p;
 }
 
@@ -188,24 +206,55 @@ int launch_smem(socp_ctx *ctx, K kernel, int grid, int threads, size_t smem, con
     return SOCP_OK;
 }
 
+int launch_qpass(socp_ctx *ctx, int grid, size_t smem, const SolverDev &D, int cur) {
+    if (smem > 48 * 1024) {
+        size_t &have = ctx->smem_configured[(const void *)hybrd_qpass_kernel];
+        if (smem > have) {
+            cudaError_t e = cudaFuncSetAttribute(hybrd_qpass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) {
+                ctx->err = std::string("cudaFuncSetAttribute(hybrd_qpass_kernel): ") + cudaGetErrorString(e);
+                ctx->launch_error = SOCP_ERR_CUDA;
+                return SOCP_ERR_CUDA;
+            }
+            have = smem;
+        }
+    }
+    hybrd_qpass_kernel<<<grid, 128, smem, ctx->stream>>>(D, cur);
+    return SOCP_OK;
+}
+
 void launch_hybrd(socp_ctx *ctx, const SolverDev &D, int cur, int grid, int prof_slot) {
     const SmemPlan sp = smem_plan(D);
     const int thr = (sp.G == 32) ? 32 * sp.groups : 128;
     const int g = (sp.G == 32) ? grid * (4 / sp.groups) : grid;
     if (sp.G == 32) {
+        if (prof_slot >= 0) cudaEventRecord(prof_event(ctx, kProfEv * prof_slot + 3), ctx->stream);
         if (sp.stage_r) launch_smem(ctx, hybrd_res_kernel<32, true>, g, thr, sp.bytes_res, D, cur, sp.doubles_res);
         else launch_smem(ctx, hybrd_res_kernel<32, false>, g, thr, sp.bytes_res, D, cur, sp.doubles_res);
-        if (prof_slot >= 0) cudaEventRecord(prof_event(ctx, kProfEv * prof_slot + 3), ctx->stream);
+        if (prof_slot >= 0) cudaEventRecord(prof_event(ctx, kProfEv * prof_slot + 4), ctx->stream);
         if (sp.stage_q_jac) launch_smem(ctx, hybrd_jac_kernel<32, true, true>, g, thr, sp.bytes_jac, D, cur, sp.doubles_jac);
         else if (sp.stage_r) launch_smem(ctx, hybrd_jac_kernel<32, true, false>, g, thr, sp.bytes_jac, D, cur, sp.doubles_jac);
         else launch_smem(ctx, hybrd_jac_kernel<32, false, false>, g, thr, sp.bytes_jac, D, cur, sp.doubles_jac);
     } else {
+        const bool full = g == D.sm_count * 6;
+        if (sp.split) {
+            // Q pass: one CTA per problem, a whole number of waves of resident CTAs when the round is full
+            const int gq = full ? D.sm_count * sp.qpass_per_sm * 2 : g;
+            launch_qpass(ctx, gq, sp.bytes_qpass, D, cur);
+            if (prof_slot >= 0) cudaEventRecord(prof_event(ctx, kProfEv * prof_slot + 3), ctx->stream);
+            // chain kernel: one warp (= one 32-thread CTA) per problem
+            const int gc = full ? D.sm_count * sp.chain_per_sm * 2 : g;
+            launch_smem(ctx, hybrd_chain_kernel<true>, gc, 32, (size_t)sp.chain_doubles * 8, D, cur, sp.chain_doubles);
+            ctx->launches += 1;
+        } else {
+        if (prof_slot >= 0) cudaEventRecord(prof_event(ctx, kProfEv * prof_slot + 3), ctx->stream);
         // the round grid is 6 CTAs per SM (two waves of the 3-CTA/SM Jacobian phase); the Broyden phase holds
         // 4 CTAs/SM (P = 85), so a full grid becomes 8 per SM: two full waves again
-        const int g_res = (g == D.sm_count * 6) ? D.sm_count * 8 : g;
+        const int g_res = full ? D.sm_count * 8 : g;
         if (sp.stage_r) launch_smem(ctx, hybrd_res_kernel<128, true>, g_res, thr, sp.bytes_res, D, cur, sp.doubles_res);
         else launch_smem(ctx, hybrd_res_kernel<128, false>, g_res, thr, sp.bytes_res, D, cur, sp.doubles_res);
-        if (prof_slot >= 0) cudaEventRecord(prof_event(ctx, kProfEv * prof_slot + 3), ctx->stream);
+        }
+        if (prof_slot >= 0) cudaEventRecord(prof_event(ctx, kProfEv * prof_slot + 4), ctx->stream);
         if (sp.stage_q_jac && sp.jac_r_global)          // R straight to global memory: one more CTA per SM
             launch_smem(ctx, hybrd_jac_kernel<128, false, true>, g, thr, (size_t)(sp.doubles_jac - D.LR) * 8, D, cur, sp.doubles_jac - D.LR);
         else if (sp.stage_q_jac) launch_smem(ctx, hybrd_jac_kernel<128, true, true>, g, thr, sp.bytes_jac, D, cur, sp.doubles_jac);
@@ -235,7 +284,7 @@ void launch_round(socp_ctx *ctx, const SolverDev &D, int cur, int grid_int, int 
     assemble_kernel<MODEL><<<grid_int, 128, 0, ctx->stream>>>(D, cur);
     if (prof_slot >= 0) cudaEventRecord(prof_event(ctx, kProfEv * prof_slot + 2), ctx->stream);
     launch_hybrd(ctx, D, cur, grid_adv, prof_slot);
-    if (prof_slot >= 0) cudaEventRecord(prof_event(ctx, kProfEv * prof_slot + 4), ctx->stream);
+    if (prof_slot >= 0) cudaEventRecord(prof_event(ctx, kProfEv * prof_slot + 5), ctx->stream);
     ctx->launches += 4;
     ctx->rounds += 1;
 }
