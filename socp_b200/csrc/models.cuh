@@ -43,15 +43,17 @@ template <> struct Model<GODDARD> {
 
     // goddard.cpp:188-253 (true singular control), expression order of the reference.  Out of line:
     // it is only reached with mu2 == 0 inside the switching window, and inlining its ~600 instructions
-    // into every RHS copy of the RK4 loop overflows the instruction cache.
-    __device__ __noinline__ static double singular(const Ctx &c, const double *X) {
-        double x = X[0], y = X[1], z = X[2], vx = X[3], vy = X[4], vz = X[5], mass = X[6];
-        double p_x = X[7], p_y = X[8], p_z = X[9], p_vx = X[10], p_vy = X[11], p_vz = X[12];
+    // into every RHS copy of the RK4 loop overflows the instruction cache.  Every operand travels BY VALUE:
+    // with pointer arguments (the state array, the context) the caller had to keep both in addressable local
+    // memory, and the compiler stored the whole state to the stack in every RHS evaluation for a call that
+    // the benchmark workload never makes (mu2 > 0): 60 STL sites, 19.5 % of the LSU bandwidth of the RK4 kernel.
+    __device__ __noinline__ static double singular(double b, double C, double KD, double kr,
+                                                   double x, double y, double z, double vx, double vy, double vz, double mass,
+                                                   double p_x, double p_y, double p_z, double p_vx, double p_vy, double p_vz) {
         double r = sqrt(x * x + y * y + z * z);
         double v = sqrt(vx * vx + vy * vy + vz * vz);
         double rdotv = x * vx + y * vy + z * vz;
         double pvdotv = p_vx * vx + p_vy * vy + p_vz * vz;
-        double b = c.b, C = c.C, KD = c.KD, kr = c.kr;
         double g = 1 / r / r;
         double norm_pv = sqrt(p_vx * p_vx + p_vy * p_vy + p_vz * p_vz);
         double ex = exp(-kr * (r - 1));
@@ -93,7 +95,10 @@ template <> struct Model<GODDARD> {
             if (Switch < 0) alpha_u = -Switch * c.half_inv_mu2;
         } else {
             if (t <= c.sw0) alpha_u = 1.0;
-            else if (t <= c.sw1) alpha_u = (c.sing < 0) ? singular(c, X) : c.sing;
+            else if (t <= c.sw1)
+                alpha_u = (c.sing < 0) ? singular(c.b, c.C, c.KD, c.kr, X[0], X[1], X[2], X[3], X[4], X[5], X[6], X[7], X[8], X[9],
+                                                  p_vx, p_vy, p_vz)
+                                       : c.sing;
         }
         double a = fabs(alpha_u);
         double scale = -alpha_u * pvinv;            // u = -p_v * alpha_u / |p_v|

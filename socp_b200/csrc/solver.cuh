@@ -62,6 +62,7 @@ struct SolverDev {
     int *counts;
     unsigned long long *counters;      // [0] RK4 steps, [1] Broyden iterations, [2] Jacobian factorisations, [3] dopri steps,
                                        // [4] residual requests, [16+k] / [32+k] phase clocks
+    int jac_fast;                      // Jacobian phase: 1 = qrfac_w / qform_w + bulk copies of Q (128-thread CTA, Q in shared memory)
     int sm_count;                      // multiprocessors of the device (seq_warp)
     int phase_clocks;                  // debugging aid (SOCP_PHASE_CLOCKS=1): accumulate clock64() per phase
 };
@@ -756,9 +757,9 @@ SOCP_DEV void axpy_sub4(double *y, const double *x, double t, int m) {
     for (; i + 3 < m; i += 4) {
         const double x0 = x[i], x1 = x[i + 1], x2 = x[i + 2], x3 = x[i + 3];
         const double y0 = y[i], y1 = y[i + 1], y2 = y[i + 2], y3 = y[i + 3];
-        y[i] = y0 - t * x0; y[i + 1] = y1 - t * x1; y[i + 2] = y2 - t * x2; y[i + 3] = y3 - t * x3;
+        y[i] = __fma_rn(-t, x0, y0); y[i + 1] = __fma_rn(-t, x1, y1); y[i + 2] = __fma_rn(-t, x2, y2); y[i + 3] = __fma_rn(-t, x3, y3);
     }
-    for (; i < m; ++i) y[i] -= t * x[i];
+    for (; i < m; ++i) y[i] = __fma_rn(-t, x[i], y[i]);
 }
 
 // qrfac (no pivoting) fused with "qtf = Q^T fvec" (the Householder reflections are applied to
@@ -812,6 +813,141 @@ __device__ void qrfac_g(int n, double *a, int lda, double *rdiag, double *acnorm
             }
         }
         if (tid == 0) rdiag[j] = -ajnorm;
+        gsync<G>();
+    }
+}
+
+// ---- the same two routines for a 128-thread CTA, built for latency: one CTA barrier per Householder step
+// (three / two above) and four lanes per column.
+// * Every warp forms the reflector of step j REDUNDANTLY from column j (norm, sign, scaling) into its own
+//   buffer -- same bits in every warp, no barrier between norm, scaling and application.  The scaled column is
+//   written back by one warp at the start of the next step, when nobody reads it any more.
+// * Application: a column is owned by FOUR lanes; lane q accumulates the elements e = q (mod 4) -- exactly the
+//   four running sums of dot4 -- and two shuffles form (s0 + s1) + (s2 + s3): the factors are bit for bit
+//   those of qrfac_g / qform_g (and so of the dense MINPACK loops, up to the sign of a zero).
+// vbuf: [2][G/32][n] doubles of shared memory (qform double-buffers the reflector).
+SOCP_DEV double quarter_partial(const double *v, const double *c, int len, int q) {
+    const int m4 = len & ~3;
+    double s = 0.;
+    for (int e = q; e < m4; e += 4) s = fma(v[e], c[e], s);
+    if (q == 0) for (int e = m4; e < len; ++e) s = fma(v[e], c[e], s);      // dot4 puts the tail on its first sum
+    return s;
+}
+// (s0 + s1) + (s2 + s3) over the four lanes of a column; executed by every lane of the warp at ONE site
+SOCP_DEV double quarter_reduce(double s) {
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    return s;
+}
+
+template <int G>
+__device__ void qrfac_w(int n, double *a, int lda, double *rdiag, double *acnorm, double *qtf, double *vbuf, int rot, int *hi) {
+    constexpr int NW = G / 32;
+    const int tid = (threadIdx.x + 32 * rot) % G;
+    const int warp = tid >> 5, lane = tid & 31, c = lane >> 2, q = lane & 3;
+    double *vb = vbuf + (size_t)warp * n;
+    gsync<G>();
+    for (int j = warp; j < n; j += NW) {               // column norms, one warp per column
+        const double v = enorm_warp(n, a + (size_t)j * lda);
+        if (lane == 0) acnorm[j] = v;
+    }
+    for (int k = tid; k <= n; k += G) {                // last non-zero row of every column (qtf: dense)
+        int last = (k < n) ? 0 : n - 1;
+        if (k < n) {
+            const double *ck = a + (size_t)k * lda;
+            for (int i = n - 1; i > 0; --i) if (ck[i] != 0.) { last = i; break; }
+        }
+        hi[k] = last;
+    }
+    gsync<G>();
+    int wb_j = -1, wb_len = 0;                         // reflector still to be written back into its column
+    for (int j = 0; j < n; ++j) {
+        if (wb_j >= 0 && warp == (wb_j % NW)) {        // nobody reads column wb_j below its diagonal any more
+            double *cw = a + (size_t)wb_j * lda + wb_j;
+            for (int e = lane; e < wb_len; e += 32) cw[e] = vb[e];
+        }
+        __syncwarp();
+        wb_j = -1;
+        double *cj = a + (size_t)j * lda;
+        const int hj = max(hi[j], j), len = hj - j + 1;
+        double ajnorm = enorm_warp(len, cj + j);
+        if (ajnorm != 0.) {
+            if (cj[j] < 0.) ajnorm = -ajnorm;
+            for (int e = lane; e < len; e += 32) {
+                double v = cj[j + e] / ajnorm;
+                if (e == 0) v += 1.;
+                vb[e] = v;
+            }
+            __syncwarp();
+            const double ajj = vb[0];
+            for (int k0 = j + 1 + warp * 8; k0 <= n; k0 += 8 * NW) {     // remaining columns, and qtf as column n
+                const int k = k0 + c;
+                const bool active = k <= n;
+                double *ck = (k < n) ? a + (size_t)k * lda + j : qtf + j;
+                const double sum = quarter_reduce(active ? quarter_partial(vb, ck, len, q) : 0.);
+                if (active && sum != 0.) {
+                    const double temp = sum / ajj;
+                    for (int e = q; e < len; e += 4) ck[e] = __fma_rn(-temp, vb[e], ck[e]);
+                    if (q == 0 && hi[k] < hj) hi[k] = hj;
+                }
+            }
+            wb_j = j; wb_len = len;
+        }
+        if (tid == 0) rdiag[j] = -ajnorm;
+        gsync<G>();
+    }
+    if (wb_j >= 0 && warp == (wb_j % NW)) {
+        double *cw = a + (size_t)wb_j * lda + wb_j;
+        for (int e = lane; e < wb_len; e += 32) cw[e] = vb[e];
+    }
+    gsync<G>();
+}
+
+template <int G>
+__device__ void qform_w(int n, double *qm, int lda, double *vbuf, int rot, const int *hi) {
+    constexpr int NW = G / 32;
+    const int tid = (threadIdx.x + 32 * rot) % G;
+    const int warp = tid >> 5, lane = tid & 31, c = lane >> 2, q = lane & 3;
+    for (int j = 1 + tid; j < n; j += G)
+        for (int i = 0; i < j; ++i) qm[i + (size_t)j * lda] = 0.;
+    // reflector k lives in column k, rows k..hk, and no step before its own touches it: every warp copies the
+    // NEXT reflector into its spare buffer before the barrier that ends a step, so the owner of column k may
+    // overwrite it (with H_k e_k) right after that barrier
+    {
+        const int k = n - 1, len = max(hi[k], k) - k + 1;
+        double *vb = vbuf + (size_t)warp * n;
+        for (int e = lane; e < len; e += 32) vb[e] = qm[(size_t)k * lda + k + e];
+    }
+    gsync<G>();
+    for (int l = 0; l < n; ++l) {
+        const int k = n - 1 - l;
+        const int hk = max(hi[k], k), len = hk - k + 1;
+        const double *vb = vbuf + ((size_t)(l & 1) * NW + warp) * n;
+        if (k > 0) {
+            const int k2 = k - 1, len2 = max(hi[k2], k2) - k2 + 1;
+            double *nb = vbuf + ((size_t)((l + 1) & 1) * NW + warp) * n;
+            for (int e = lane; e < len2; e += 32) nb[e] = qm[(size_t)k2 * lda + k2 + e];
+        }
+        const double wk = vb[0];
+        if (wk != 0.) {
+            for (int j0 = k + warp * 8; j0 < n; j0 += 8 * NW) {
+                const int j = j0 + c;
+                const bool active = j < n;
+                double *cj = qm + (size_t)j * lda + k;
+                // column k is e_k here (never stored): dot4's four sums are (w_k, 0, 0, 0), the update is e_k - (w_k / w_k) w
+                double part = 0.;
+                if (j == k) part = (q == 0) ? vb[0] : 0.;
+                else if (active) part = quarter_partial(cj, vb, len, q);
+                const double sum = quarter_reduce(part);
+                if (active && sum != 0.) {
+                    const double temp = sum / wk;
+                    if (j == k) for (int e = q; e < len; e += 4) cj[e] = __fma_rn(-temp, vb[e], (e == 0) ? 1. : 0.);
+                    else for (int e = q; e < len; e += 4) cj[e] = __fma_rn(-temp, vb[e], cj[e]);
+                }
+            }
+        } else if (warp == 0 && c == 0) {
+            for (int e = q; e < len; e += 4) qm[(size_t)k * lda + k + e] = (e == 0) ? 1. : 0.;
+        }
         gsync<G>();
     }
 }
@@ -1429,7 +1565,7 @@ __device__ void dogleg_and_request(const SolverDev &D, long b, const Work &W, in
 // shared-memory carve for one group: [13 P vectors][R][Q]
 template <int G>
 SOCP_DEV double *group_smem(const SolverDev &D, int per_group_doubles) {
-    extern __shared__ double smem_all[];
+    extern __shared__ __align__(128) double smem_all[];
     const int grp = (G == 32) ? (threadIdx.x >> 5) : 0;
     return smem_all + (size_t)grp * per_group_doubles;
 }
@@ -1702,6 +1838,16 @@ hybrd_jac_kernel(SolverDev D, int cur, int per_group_doubles) {
     int *next_res = D.lists + (size_t)((1 - cur) * 2 + 0) * D.B;
     int *next_cnt = D.counts + (1 - cur) * 2;
     const int ldq_s = n | 1;                               // odd leading dimension in shared memory
+    // fast form (128-thread CTA, Q staged): Q travels by bulk copy when its shared layout equals the global
+    // one (odd P), the reflector buffers of qrfac_w / qform_w follow Q in shared memory
+    const bool fast = (G == 128) && STAGE_Q && D.jac_fast;
+    const bool bulk = fast && ldq_s == n;
+    __shared__ unsigned long long jac_bar;
+    unsigned jac_parity = 0;
+    if (bulk) {
+        if (threadIdx.x == 0) mbar_init(&jac_bar, 1);
+        __syncthreads();
+    }
 
     for (long g = (long)blockIdx.x * GROUPS + grp; g < njac; g += (long)gridDim.x * GROUPS) {
         const long b = jac_list[g];
@@ -1719,14 +1865,27 @@ hybrd_jac_kernel(SolverDev D, int cur, int per_group_doubles) {
         W.r = STAGE_R ? after : D.r + (size_t)b * D.LR;
         if (STAGE_R) after += D.LR;
         double *gq = D.fjac + (size_t)b * D.QS;
+        if (STAGE_Q) after = sm + (((after - sm) + 1) & ~(ptrdiff_t)1);      // Q starts 16-byte aligned (bulk copies)
         W.q = STAGE_Q ? after : gq;
         W.ldq = STAGE_Q ? ldq_s : n;
         long long phase_t0 = clock64();
         gcopy_async<G>(W.x, D.x + b * n, n); gcopy_async<G>(W.fvec, D.fvec + b * n, n); gcopy_async<G>(W.diag, D.diag + b * n, n);
-        if (STAGE_Q)
+        double *vbuf = nullptr;
+        if (STAGE_Q) vbuf = W.q + (((size_t)ldq_s * n + 1) & ~(size_t)1);      // [2][G/32][n] reflector buffers (fast form)
+        if (bulk) {
+            if (tid == 0) {
+                bulk_wait_read();                          // the previous problem's copy out has read the buffer
+                mbar_expect_tx(&jac_bar, (unsigned)D.QS * 8u);
+                bulk_g2s(W.q, gq, (unsigned)D.QS * 8u, &jac_bar);
+            }
+        } else if (STAGE_Q)
             for (int c = tid >> 5; c < n; c += G / 32)
                 for (int i = tid & 31; i < n; i += 32) __pipeline_memcpy_async(W.q + i + (size_t)c * ldq_s, gq + i + (size_t)c * n, sizeof(double));
         gcopy_async_wait();
+        if (bulk) {
+            while (!mbar_try_wait(&jac_bar, jac_parity)) {}
+            jac_parity ^= 1u;
+        }
         gsync<G>();
         SOCP_PHASE(32, 0);
         if (tid == 0) {
@@ -1739,7 +1898,8 @@ hybrd_jac_kernel(SolverDev D, int cur, int per_group_doubles) {
         for (int i = tid; i < n; i += G) W.qtf[i] = W.fvec[i];
         // wa1 = rdiag, wa2 = acnorm
         int *hi = (int *)W.scr;                            // [n + 1] last non-zero row per column (scr is free here)
-        qrfac_g<G>(n, W.q, W.ldq, W.wa1, W.wa2, W.qtf, red, seq_warp<G>(D.sm_count), hi);
+        if (fast) qrfac_w<G>(n, W.q, W.ldq, W.wa1, W.wa2, W.qtf, vbuf, seq_warp<G>(D.sm_count), hi);
+        else qrfac_g<G>(n, W.q, W.ldq, W.wa1, W.wa2, W.qtf, red, seq_warp<G>(D.sm_count), hi);
         SOCP_PHASE(32, 1);
         if (is[I_ITER] == 1) {
             for (int j = tid; j < n; j += G) {
@@ -1757,7 +1917,8 @@ hybrd_jac_kernel(SolverDev D, int cur, int per_group_doubles) {
         }
         pack_r_g<G>(n, W.q, W.ldq, W.wa1, W.r);
         SOCP_PHASE(32, 2);
-        qform_g<G>(n, W.q, W.ldq, W.wa1, seq_warp<G>(D.sm_count), hi);
+        if (fast) qform_w<G>(n, W.q, W.ldq, vbuf, seq_warp<G>(D.sm_count), hi);
+        else qform_g<G>(n, W.q, W.ldq, W.wa1, seq_warp<G>(D.sm_count), hi);
         SOCP_PHASE(32, 3);
         for (int j = tid; j < n; j += G) W.diag[j] = fmax(W.diag[j], W.wa2[j]);
         gsync<G>();
@@ -1767,12 +1928,18 @@ hybrd_jac_kernel(SolverDev D, int cur, int per_group_doubles) {
         gcopy<G>(D.qtf + b * n, W.qtf, n); gcopy<G>(D.wa1 + b * n, W.wa1, n);
         if (STAGE_R) gcopy<G>(D.r + (size_t)b * D.LR, W.r, D.LR);
         SOCP_PHASE(32, 5);
-        if (STAGE_Q)
+        if (bulk) {
+            // the accumulated Q leaves with one bulk copy; the next problem's copy in waits for it to have read the buffer
+            fence_async_smem();
+            gsync<G>();
+            if (tid == 0) bulk_s2g(gq, W.q, (unsigned)D.QS * 8u);
+        } else if (STAGE_Q)
             for (int c = tid >> 5; c < n; c += G / 32)
                 for (int i = tid & 31; i < n; i += 32) gq[i + (size_t)c * n] = W.q[i + (size_t)c * ldq_s];
         gsync<G>();
         SOCP_PHASE(32, 6);
     }
+    if (bulk && threadIdx.x == 0) bulk_wait_all();
 }
 
 // ---- small kernels -------------------------------------------------------------------------------

@@ -156,8 +156,10 @@ SmemPlan smem_plan(const SolverDev &D) {
     p.G = (D.P <= 32) ? 32 : 128;
     p.stage_r = (base + D.LR) * 8 <= limit;
     const size_t dr = base + (p.stage_r ? D.LR : 0);
-    p.stage_q_jac = p.stage_r && (dr + ldq * D.P) * 8 <= limit;
-    const size_t dj = dr + (p.stage_q_jac ? ldq * D.P : 0);
+    // Jacobian phase with Q staged: [vectors][R][pad to 16 B][Q, ld = P | 1][8 P reflector buffers of qrfac_w / qform_w]
+    const size_t qs_jac = 1 + ((ldq * D.P + 1) & ~(size_t)1) + 8 * (size_t)D.P;
+    p.stage_q_jac = p.stage_r && (dr + qs_jac) * 8 <= limit;
+    const size_t dj = dr + (p.stage_q_jac ? qs_jac : 0);
     p.doubles_res = (int)dr;
     p.doubles_jac = (int)dj;
     p.groups = 1;
@@ -351,6 +353,10 @@ int run_solver(socp_ctx *ctx, const socp_shape *shape, long B, const double *d_m
     D.counters = ctx->d_counters;
     D.sm_count = ctx->sm_count;
     D.phase_clocks = getenv("SOCP_PHASE_CLOCKS") ? 1 : 0;
+    {
+        const char *jm = getenv("SOCP_JAC");               // SOCP_JAC=old: the three-barrier Householder routines (A/B runs)
+        D.jac_fast = !(jm && !strcmp(jm, "old"));
+    }
     const int grid_int = ctx->sm_count * 8;
     const int grid_adv = ctx->sm_count * 6;
     // debugging aid: SOCP_ROUND_LOG=<file> (with profiling on) logs every round: index, residual and
