@@ -771,21 +771,46 @@ def run_stage2(args, eng, torch, dist, dev, w1, pool):
                                 "sample": "first %d problems of the same batch, one process per core, wall time" % n_par}
     out["warm_start"] = warm
 
-    # (b) continuation KD 0 -> 310, step 1 (shooting.cpp:695-778) on the members that converged in (a)
+    # (b) continuation KD 0 -> 310, step 1 (shooting.cpp:695-778) on the members that converged in (a).
+    # Device resident: the warm-started solutions stay in HBM and the homotopy state machines run on the device
+    # (socp_continuation_param_batch, mem = SOCP_DEVICE); the host-buffer form is timed beside it as e2e.
     ok = np.flatnonzero(info == 1)
     if ok.size:
         kd = S.pidx(S.GODDARD, "KD")
-        goal = np.full(ok.size, 310.0)
-        xs = np.ascontiguousarray(x[ok])
-        args_c = (w.shape, np.ascontiguousarray(w.mp[ok]), np.ascontiguousarray(w.time[ok]), np.ascontiguousarray(w.Xb[ok]), xs, 1.0, kd, goal)
-        eng.continuation_param_batch(*args_c, xtol=w.xtol)                  # warm-up
+        okd = torch.from_numpy(ok).to(dev)
+        sel_d = lambda t: t.index_select(0, okd).contiguous()
+        c_mp0, c_time, c_Xb, c_x0 = sel_d(d["mp"]), sel_d(d["time"]), sel_d(d["Xb"]), sel_d(d["x"])
+        c_goal = torch.full((ok.size,), 310.0, dtype=torch.float64, device=dev)
+        c_info = torch.empty(ok.size, dtype=torch.int32, device=dev)
+        c_calls = torch.empty((ok.size, 2), dtype=torch.int32, device=dev)
+        c_mp, c_x = torch.empty_like(c_mp0), torch.empty_like(c_x0)
+
+        def cont_step():
+            c_mp.copy_(c_mp0); c_x.copy_(c_x0)
+            eng.continuation_param_batch(w.shape, c_mp, c_time, c_Xb, c_x, 1.0, kd, c_goal, xtol=w.xtol, info=c_info, calls=c_calls)
+        cont_step()                                                         # warm-up
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.e2e_steps):
+            cont_step()
+        e1.record()
+        torch.cuda.synchronize()
+        dt = e0.elapsed_time(e1) * 1e-3 / args.e2e_steps
+        r = dict(info=c_info.cpu().numpy(), calls=c_calls.cpu().numpy(), x=c_x.cpu().numpy())
+        # the same through host buffers (staged once in, once out by the library)
+        h_args = (w.shape, np.ascontiguousarray(w.mp[ok]), np.ascontiguousarray(w.time[ok]), np.ascontiguousarray(w.Xb[ok]),
+                  np.ascontiguousarray(x[ok]), 1.0, kd, np.full(ok.size, 310.0))
         t0 = time.perf_counter()
-        r = eng.continuation_param_batch(*args_c, xtol=w.xtol)
-        dt = time.perf_counter() - t0
+        rh = eng.continuation_param_batch(*h_args, xtol=w.xtol)
+        dth = time.perf_counter() - t0
         cont = {"workload": "goddard continuation KD 0 -> 310, step 1 (tests/testGoddard.cpp:105) on the %d members converged "
                             "in the warm-started stage" % ok.size,
                 "value": ok.size / dt, "unit": "continuations/s", "seconds": dt,
-                "api": "socp_continuation_param_batch (host buffers: staging inside the timed region)",
+                "api": "socp_continuation_param_batch(mem=SOCP_DEVICE): homotopy state machines on the device, no problem data over PCIe",
+                "e2e": {"value": ok.size / dth, "unit": "continuations/s", "api": "socp_continuation_param_batch(mem=SOCP_HOST)",
+                        "same_outcome_as_device": bool(np.array_equal(rh["info"], r["info"]) and np.array_equal(rh["calls"], r["calls"])
+                                                       and np.array_equal(rh["x"], r["x"]))},
                 "converged_fraction": float((r["info"] == 1).mean()),
                 "mean_solver_calls": float(r["calls"][:, 0].mean()), "mean_nfev_total": float(r["calls"][:, 1].mean())}
         if n_par:

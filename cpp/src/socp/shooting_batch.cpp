@@ -191,7 +191,7 @@ long shooting_batch::SolveOCP(real const& continuationStep) {
 	std::vector<int> calls(2 * B);
 	if (socp_continuation_boundary_batch(ctx, &data->shape, B, data->mparams.data(), data->time_prec.data(), data->X_prec.data(),
 	                                     data->timed.data(), data->Xd.data(), data->param.data(), data->xtol, data->maxfev,
-	                                     continuationStep, data->stepMin, data->info.data(), calls.data()) != SOCP_OK)
+	                                     continuationStep, data->stepMin, data->info.data(), calls.data(), SOCP_HOST) != SOCP_OK)
 		fail(ctx, "socp_continuation_boundary_batch");
 	const size_t nodes = data->numMulti + 1, n = data->dim;
 	for (long k = 0; k < B; k++) {
@@ -213,7 +213,7 @@ long shooting_batch::SolveOCP(real const& continuationStep, int paramIndex, std:
 	std::vector<int> calls(2 * B);
 	if (socp_continuation_param_batch(ctx, &data->shape, B, data->mparams.data(), data->time.data(), data->X.data(),
 	                                  data->param.data(), data->xtol, data->maxfev, continuationStep <= 0 ? 1.0 : continuationStep,
-	                                  paramIndex, goal.data(), data->stepMin, data->info.data(), calls.data()) != SOCP_OK)
+	                                  paramIndex, goal.data(), data->stepMin, data->info.data(), calls.data(), SOCP_HOST) != SOCP_OK)
 		fail(ctx, "socp_continuation_param_batch");
 	for (long k = 0; k < B; k++) { data->calls[k] = calls[2 * k]; data->nfev[k] = calls[2 * k + 1]; }
 	return count_ok(data->info);

@@ -12,8 +12,10 @@
  * (0 = ok, <0 = error, message via socp_last_error); no exceptions cross the boundary; all work is
  * ordered on the context's CUDA stream; one context per GPU and per host thread.
  * `mem` selects where the caller's buffers live: SOCP_HOST (the library stages H2D / D2H itself)
- * or SOCP_DEVICE (device pointers on the context's device; the call is asynchronous on the
- * context stream until socp_sync()).  There is no CPU fallback: without a CUDA device
+ * or SOCP_DEVICE (device pointers on the context's device; results are ordered on the context
+ * stream: socp_sync() before reading them from another stream).  The batched solves and continuations
+ * block the calling host thread intermittently: the round loop reads device-side work counters every
+ * few rounds to know when the last problem has retired; the trajectory / residual / Jacobian calls only enqueue.  There is no CPU fallback: without a CUDA device
  * socp_create fails.
  *
  * Data layouts (all double unless noted, row-major, one problem after another):
@@ -190,19 +192,22 @@ int socp_solve_hybrj_batch(socp_ctx *ctx, const socp_shape *shape, long B, const
 /* shooting::SolveShootingContinuation on a model parameter (shooting.cpp:695-778), every problem
  * running its own homotopy b in (0,1] with step halving.  mparams is updated in place (entry
  * param_idx ends at goal[b] on success).  goal is [B].  calls is [B][2] = {solver calls, total
- * nfev}.  Host buffers only. */
+ * nfev} (may be NULL).  The per-problem state machines (b, b_prec, the accepted solution, the data of the next
+ * pass) live on the device: with mem == SOCP_DEVICE no problem data crosses PCIe at all, with SOCP_HOST the
+ * arrays are staged once before the first pass and fetched once after the last.  The call returns when every
+ * homotopy has ended (the host reads one counter per pass). */
 int socp_continuation_param_batch(socp_ctx *ctx, const socp_shape *shape, long B, double *mparams,
                                   const double *time, const double *Xb, double *x, double xtol,
                                   int maxfev, double step, int param_idx, const double *goal,
-                                  double step_min, int *info, int *calls);
+                                  double step_min, int *info, int *calls, int mem);
 
 /* shooting::SolveShootingContinuation on the boundary data (shooting.cpp:598-692): homotopy from
- * (time_prec, Xb_prec) to (time_des, Xb_des).  Host buffers only. */
+ * (time_prec, Xb_prec) to (time_des, Xb_des).  Same conventions. */
 int socp_continuation_boundary_batch(socp_ctx *ctx, const socp_shape *shape, long B,
                                      const double *mparams, const double *time_prec,
                                      const double *Xb_prec, const double *time_des,
                                      const double *Xb_des, double *x, double xtol, int maxfev,
-                                     double step, double step_min, int *info, int *calls);
+                                     double step, double step_min, int *info, int *calls, int mem);
 
 /* FP64 FMA peak of the device measured with a register-resident DFMA chain (GFLOP/s). */
 int socp_measure_fp64_peak(socp_ctx *ctx, double *gflops, double *sm_clock_mhz);

@@ -83,8 +83,8 @@ def lib():
     L.socp_traj_var_batch.argtypes = [vp, ci, ci, cl, vp, vp, vp, vp, vp, ci]
     L.socp_jacobian_batch.argtypes = [vp, sp, cl, vp, vp, vp, vp, vp, ci]
     L.socp_solve_hybrj_batch.argtypes = [vp, sp, cl, vp, vp, vp, vp, cd, ci, vp, vp, vp, vp, ci]
-    L.socp_continuation_param_batch.argtypes = [vp, sp, cl, vp, vp, vp, vp, cd, ci, cd, ci, vp, cd, vp, vp]
-    L.socp_continuation_boundary_batch.argtypes = [vp, sp, cl, vp, vp, vp, vp, vp, vp, cd, ci, cd, cd, vp, vp]
+    L.socp_continuation_param_batch.argtypes = [vp, sp, cl, vp, vp, vp, vp, cd, ci, cd, ci, vp, cd, vp, vp, ci]
+    L.socp_continuation_boundary_batch.argtypes = [vp, sp, cl, vp, vp, vp, vp, vp, vp, cd, ci, cd, cd, vp, vp, ci]
     L.socp_measure_fp64_peak.argtypes = [vp, P(cd), P(cd)]
     for name in SYMBOLS:
         f = getattr(L, name)

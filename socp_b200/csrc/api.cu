@@ -122,7 +122,7 @@ static int fetch_out(socp_ctx *ctx, T *dst, const T *dev, size_t count, int mem)
 
 enum { SLOT_MPARAMS = 0, SLOT_SW, SLOT_T0, SLOT_TF, SLOT_X0, SLOT_XF, SLOT_AUX0, SLOT_AUX1, SLOT_AUX2,
        SLOT_TIME, SLOT_XB, SLOT_X, SLOT_FVEC, SLOT_FJAC, SLOT_INFO, SLOT_NFEV, SLOT_FNORM, SLOT_PEAK,
-       SLOT_SOLVER_BASE };
+       SLOT_CONT, SLOT_CONT_A, SLOT_CONT_B, SLOT_SOLVER_BASE };
 
 template <int MODEL>
 static void launch_traj(socp_ctx *ctx, long B, int S, const double *mp, const double *sw, const double *t0,

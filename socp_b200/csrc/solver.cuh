@@ -1004,6 +1004,38 @@ __device__ void rmulv_g(int n, const double *r, const double *v, const double *a
     gsync<G>();
 }
 
+// The same product for a packed factor that lives in GLOBAL memory (one warp per problem, 16 problems per SM):
+// a row per step with the lanes along it -- consecutive lanes, consecutive addresses -- and a butterfly per row;
+// four rows are in flight so that the shuffle latencies overlap.  (The thread-per-row form above touches 32
+// different lines per load when R is not in shared memory.)
+SOCP_DEV void rmulv_rows(int n, const double *r, const double *v, const double *add, double *y) {
+    const int lane = threadIdx.x & 31;
+    __syncwarp();
+    for (int i0 = 0; i0 < n; i0 += 4) {
+        double p[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u;
+            p[u] = 0.;
+            if (i < n) {
+                const double *row = r + rowstart(n, i);
+                const int len = n - i;
+                for (int t = lane; t < len; t += 32) p[u] = fma(row[t], v[i + t], p[u]);
+            }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) p[u] += __shfl_xor_sync(0xffffffffu, p[u], off);
+        }
+        if (lane < 4 && i0 + lane < n) {
+            const double s = (lane == 0) ? p[0] : (lane == 1) ? p[1] : (lane == 2) ? p[2] : p[3];
+            y[i0 + lane] = (add ? add[i0 + lane] : 0.) + s;
+        }
+    }
+    __syncwarp();
+}
+
 // steps j = min(32 PH + 31, n - 1) .. 32 PH of dogleg's back substitution for n <= 96 (see dogleg_g)
 template <int PH>
 SOCP_DEV void backsub_phase(int n, const double *r, const double *dinvs, const double *ds, int lane,
@@ -1024,7 +1056,7 @@ SOCP_DEV void backsub_phase(int n, const double *r, const double *dinvs, const d
 }
 
 // dogleg: x <- step; wa1, wa2 scratch
-template <int G>
+template <int G, bool RROWS = false>
 __device__ void dogleg_g(int n, const double *r, const double *diag, const double *qtb, double delta,
                          double *x, double *wa1, double *wa2, double *red, int seqw, bool clk_on = false,
                          unsigned long long *clk_counters = nullptr) {
@@ -1101,7 +1133,8 @@ __device__ void dogleg_g(int n, const double *r, const double *diag, const doubl
     if (gnorm != 0.) {
         gsync<G>();
         for (int j = tid; j < n; j += G) wa1[j] = (wa1[j] / gnorm) / diag[j];
-        rmulv_g<G>(n, r, wa1, nullptr, wa2);
+        if (RROWS) rmulv_rows(n, r, wa1, nullptr, wa2);
+        else rmulv_g<G>(n, r, wa1, nullptr, wa2);
         double temp = enorm_g<G>(n, wa2, red);
         sgnorm = (gnorm / temp) / temp;
         alpha = 0.;
@@ -1539,12 +1572,12 @@ struct Work {
 };
 
 // dogleg step from the current factors, trial point xe = x + p, and the request for F(xe)
-template <int G>
+template <int G, bool RROWS = false>
 __device__ void dogleg_and_request(const SolverDev &D, long b, const Work &W, int *is, double *ds, double *red,
                                    int *next_res, int *next_cnt) {
     const int n = D.P, tid = threadIdx.x % G;
     const double delta = ds[D_DELTA];
-    dogleg_g<G>(n, W.r, W.diag, W.qtf, delta, W.wa1, W.wa2, W.wa3, red, seq_warp<G>(D.sm_count), D.phase_clocks, D.counters);
+    dogleg_g<G, RROWS>(n, W.r, W.diag, W.qtf, delta, W.wa1, W.wa2, W.wa3, red, seq_warp<G>(D.sm_count), D.phase_clocks, D.counters);
     for (int j = tid; j < n; j += G) {
         const double pj = -W.wa1[j];
         W.wa1[j] = pj;
@@ -1641,7 +1674,9 @@ SOCP_DEV void res_loop(const SolverDev &D, int cur, int per_group_doubles) {
         double actred = -1.;
         if (fnorm1 < fnorm) { const double q = fnorm1 / fnorm; actred = 1. - q * q; }
         // predicted reduction: wa3 = qtf + R * wa1
-        rmulv_g<G>(n, W.r, W.wa1, W.qtf, W.wa3);
+        constexpr bool RROWS = SPLIT && !STAGE_R && G == 32;
+        if (RROWS) rmulv_rows(n, W.r, W.wa1, W.qtf, W.wa3);
+        else rmulv_g<G>(n, W.r, W.wa1, W.qtf, W.wa3);
         const double temp = enorm_g<G>(n, W.wa3, red);
         double prered = 0.;
         if (temp < fnorm) { const double q = temp / fnorm; prered = 1. - q * q; }
@@ -1790,7 +1825,7 @@ SOCP_DEV void res_loop(const SolverDev &D, int cur, int per_group_doubles) {
             } else r1mpyq_g<G>(n, n, W.q, W.ldq, W.scr, W.qtf);
             SOCP_PHASE(16, 5);
             if (tid == 0) is[I_JEVAL] = 0;
-            dogleg_and_request<G>(D, b, W, is, ds, red, next_res, next_cnt);
+            dogleg_and_request<G, RROWS>(D, b, W, is, ds, red, next_res, next_cnt);
             store_r = true;
             SOCP_PHASE(16, 6);
         }
@@ -1817,7 +1852,7 @@ hybrd_res_kernel(SolverDev D, int cur, int per_group_doubles) {
 // of a Broyden iteration once Q is gone are the dependent chains (Givens sweeps, back substitution, norms);
 // their latency is hidden by the other warps of the SM instead of by idle threads of the same CTA.
 template <bool STAGE_R>
-__global__ void __launch_bounds__(128, STAGE_R ? 1 : 4)
+__global__ void __launch_bounds__(32, STAGE_R ? 5 : 16)
 hybrd_chain_kernel(SolverDev D, int cur, int per_group_doubles) {
     res_loop<32, STAGE_R, true>(D, cur, per_group_doubles);
 }
@@ -1841,7 +1876,7 @@ hybrd_jac_kernel(SolverDev D, int cur, int per_group_doubles) {
     // fast form (128-thread CTA, Q staged): Q travels by bulk copy when its shared layout equals the global
     // one (odd P), the reflector buffers of qrfac_w / qform_w follow Q in shared memory
     const bool fast = (G == 128) && STAGE_Q && D.jac_fast;
-    const bool bulk = fast && ldq_s == n;
+    const bool bulk = (G == 128) && STAGE_Q && ldq_s == n;
     __shared__ unsigned long long jac_bar;
     unsigned jac_parity = 0;
     if (bulk) {
@@ -1943,8 +1978,11 @@ hybrd_jac_kernel(SolverDev D, int cur, int per_group_doubles) {
 }
 
 // ---- small kernels -------------------------------------------------------------------------------
-__global__ void solver_init(SolverDev D, const double *x_in, long first) {
-    // problems [first, first + B): copy the unknowns, reset the state, enqueue the first residual
+__global__ void solver_init(SolverDev D, const double *x_in, long first, const int *active) {
+    // problems [first, first + B): copy the unknowns, reset the state, enqueue the first residual.
+    // active != nullptr (continuation passes): only the problems whose flag is set take part; the others keep
+    // PH_IDLE and are never listed.  counts[] was zeroed by the caller; the list order is the order of the atomics
+    // (a problem's result does not depend on its position in any list).
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < D.B * D.P) {
         const double v = x_in[first * D.P + i];
@@ -1954,25 +1992,28 @@ __global__ void solver_init(SolverDev D, const double *x_in, long first) {
     if (i < D.B) {
         int *is = D.istate + i * I_COUNT;
         for (int k = 0; k < I_COUNT; ++k) is[k] = 0;
-        is[I_PHASE] = PH_F0;
-        D.lists[i] = (int)i;          // lists[0][0] = residual requests of round 0
         for (int k = 0; k < D_COUNT; ++k) D.dstate[i * D_COUNT + k] = 0.;
-    }
-    if (i == 0) {
-        D.counts[0] = (int)D.B; D.counts[1] = 0; D.counts[2] = 0; D.counts[3] = 0;
+        if (!active) {
+            is[I_PHASE] = PH_F0;
+            D.lists[i] = (int)i;                                   // lists[0][0] = residual requests of round 0
+            if (i == 0) D.counts[0] = (int)D.B;
+        } else if (active[first + i]) {
+            is[I_PHASE] = PH_F0;
+            D.lists[atomicAdd(&D.counts[0], 1)] = (int)i;
+        }
     }
 }
 
 __global__ void solver_finish(SolverDev D, long first, double *x_out, double *fvec_out, double *fjac_out,
-                              int *info, int *nfev, double *fnorm, int *njev) {
+                              int *info, int *nfev, double *fnorm, int *njev, const int *active) {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (x_out && i < D.B * D.P) x_out[first * D.P + i] = D.x[i];
+    if (x_out && i < D.B * D.P && (!active || active[first + i / D.P])) x_out[first * D.P + i] = D.x[i];
     if (fvec_out && i < D.B * D.P) fvec_out[first * D.P + i] = D.fvec[i];
     if (fjac_out && i < D.B * (long)D.P * D.P) {
         const long pp = (long)D.P * D.P;
         fjac_out[first * pp + i] = D.fjac[(i / pp) * D.QS + (i % pp)];
     }
-    if (i < D.B) {
+    if (i < D.B && (!active || active[first + i])) {
         const int *is = D.istate + i * I_COUNT;
         // a problem still in flight when the round limit is hit is NOT a hybrd outcome: it gets its own code
         // (SOCP_INFO_UNFINISHED, negative like hybrd's user-abort codes), distinct from a genuine maxfev (2)
@@ -1980,6 +2021,93 @@ __global__ void solver_finish(SolverDev D, long first, double *x_out, double *fv
         if (nfev) nfev[first + i] = is[I_NFEV];
         if (njev) njev[first + i] = is[I_NJEV];
         if (fnorm) fnorm[first + i] = D.dstate[i * D_COUNT + D_FNORM];
+    }
+}
+
+// ---- continuation on the device (shooting.cpp:598-692 boundary data, :695-778 model parameter) -----------------
+// Every problem runs the reference's homotopy loop with its own (b, b_prec): all state lives in HBM, the host
+// only launches passes and reads ONE counter (problems still in their loop) after each.
+struct ContDev {
+    long B;
+    int P, np, nt, nx;                 // unknowns, parameter block, M + 1 node times, (M + 1) dim boundary values
+    int param_idx;                     // >= 0: homotopy on mparams[param_idx]; < 0: on the boundary data
+    double step, step_min;
+    double *b, *b_prec, *rstart;       // [B] homotopy state (rstart: parameter value at b = 0)
+    const double *goal;                // [B] parameter goal
+    int *active;                       // [B] 1 while the problem is in its loop
+    int *n_active;                     // [1]
+    double *x;                         // [B][P] last accepted solution (the caller's array: result)
+    double *xw;                        // [B][P] guess in / solution out of the current pass
+    double *mparams;                   // [B][np] (param homotopy: entry param_idx is rewritten every pass)
+    const double *time_prec, *Xb_prec, *time_des, *Xb_des;     // boundary homotopy end points
+    double *time_w, *Xb_w;             // [B][nt], [B][nx] boundary data of the current pass
+    int *info_w, *nfev_w;              // [B] outcome of the current pass
+    int *info, *calls;                 // [B], [B][2] results (calls may be null)
+};
+
+// first pass set-up: b = min(step, 1), b_prec = 0, every problem active, xw = x
+__global__ void cont_begin(ContDev C) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < C.B * C.P) C.xw[i] = C.x[i];
+    if (i < C.B) {
+        C.b[i] = fmin(C.step, 1.0);
+        C.b_prec[i] = 0.;
+        C.active[i] = 1;
+        C.info[i] = 0;
+        if (C.calls) { C.calls[2 * i] = 0; C.calls[2 * i + 1] = 0; }
+        if (C.param_idx >= 0) C.rstart[i] = C.mparams[i * C.np + C.param_idx];
+        if (i == 0) *C.n_active = (int)C.B;
+    }
+}
+
+// data of the next solve for every active problem: (1 - b) prev + b desired  (shooting.cpp:609-611, :707)
+__global__ void cont_setup(ContDev C) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (C.param_idx >= 0) {
+        if (i < C.B && C.active[i]) {
+            const double bk = C.b[i];
+            C.mparams[i * C.np + C.param_idx] = (1 - bk) * C.rstart[i] + bk * C.goal[i];
+        }
+        return;
+    }
+    const int per = C.nt + C.nx;
+    if (i >= C.B * per) return;
+    const long k = i / per;
+    const int e = (int)(i % per);
+    if (!C.active[k]) return;
+    const double bk = C.b[k];
+    if (e < C.nt) C.time_w[k * C.nt + e] = (1 - bk) * C.time_prec[k * C.nt + e] + bk * C.time_des[k * C.nt + e];
+    else C.Xb_w[k * C.nx + e - C.nt] = (1 - bk) * C.Xb_prec[k * C.nx + e - C.nt] + bk * C.Xb_des[k * C.nx + e - C.nt];
+}
+
+// the homotopy state machine after a pass; one warp per problem (the P-wide copies are coalesced)
+__global__ void cont_update(ContDev C) {
+    const long k = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (k >= C.B || !C.active[k]) return;
+    const int ret = C.info_w[k];
+    double b = C.b[k], b_prec = C.b_prec[k];
+    int still = 1;
+    double *x = C.x + k * C.P, *xw = C.xw + k * C.P;
+    if (ret != 1) {
+        // failure: halve the step and restart from the last accepted solution (shooting.cpp:627-640, :731-742)
+        if (fabs(b - b_prec) < C.step_min) still = 0;
+        b = b_prec + (b - b_prec) / 2;
+        for (int j = lane; j < C.P; j += 32) xw[j] = x[j];
+    } else {
+        // success: accept, advance b by the step (capped at 1); b == 1 exactly ends the loop (:651-660, :751-759)
+        for (int j = lane; j < C.P; j += 32) x[j] = xw[j];
+        if (b == 1) still = 0;
+        else { b_prec = b; b = fmin(b + C.step, 1.0); }
+    }
+    if (lane == 0) {
+        C.info[k] = ret;
+        if (C.calls) { C.calls[2 * k] += 1; C.calls[2 * k + 1] += C.nfev_w[k]; }
+        C.b[k] = b; C.b_prec[k] = b_prec;
+        // the parameter follows b on every path but the final success, as in the reference (:635-637, :757)
+        if (C.param_idx >= 0 && !(ret == 1 && still == 0))
+            C.mparams[k * C.np + C.param_idx] = (1 - b) * C.rstart[k] + b * C.goal[k];
+        if (!still) { C.active[k] = 0; atomicSub(C.n_active, 1); }
     }
 }
 

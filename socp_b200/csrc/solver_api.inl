@@ -245,8 +245,16 @@ void launch_hybrd(socp_ctx *ctx, const SolverDev &D, int cur, int grid, int prof
             launch_qpass(ctx, gq, sp.bytes_qpass, D, cur);
             if (prof_slot >= 0) cudaEventRecord(prof_event(ctx, kProfEv * prof_slot + 3), ctx->stream);
             // chain kernel: one warp (= one 32-thread CTA) per problem
-            const int gc = full ? D.sm_count * sp.chain_per_sm * 2 : g;
-            launch_smem(ctx, hybrd_chain_kernel<true>, gc, 32, (size_t)sp.chain_doubles * 8, D, cur, sp.chain_doubles);
+            // SOCP_CHAIN_R=global: the packed factor stays in global memory (L2), 16 problems per SM instead of 5
+            static const bool r_global = getenv("SOCP_CHAIN_R") && !strcmp(getenv("SOCP_CHAIN_R"), "global");
+            if (r_global) {
+                const int cd = sp.chain_doubles - D.LR;
+                const int gc = full ? D.sm_count * 16 * 2 : g;
+                launch_smem(ctx, hybrd_chain_kernel<false>, gc, 32, (size_t)cd * 8, D, cur, cd);
+            } else {
+                const int gc = full ? D.sm_count * sp.chain_per_sm * 2 : g;
+                launch_smem(ctx, hybrd_chain_kernel<true>, gc, 32, (size_t)sp.chain_doubles * 8, D, cur, sp.chain_doubles);
+            }
             ctx->launches += 1;
         } else {
         if (prof_slot >= 0) cudaEventRecord(prof_event(ctx, kProfEv * prof_slot + 3), ctx->stream);
@@ -305,7 +313,7 @@ void launch_round_any(socp_ctx *ctx, const SolverDev &D, int cur, int gi, int ga
 int run_solver(socp_ctx *ctx, const socp_shape *shape, long B, const double *d_mparams, const double *d_time,
                const double *d_Xb, const double *d_x_in, int run_mode, double xtol, int maxfev, double epsfcn,
                double *d_x_out, double *d_fvec_out, double *d_fjac_out, int *d_info, int *d_nfev, double *d_fnorm,
-               int analytic = 0, int *d_njev = nullptr) {
+               int analytic = 0, int *d_njev = nullptr, const int *d_active = nullptr, long live_hint = -1) {
     HostPlan pl;
     int rc = make_plan(ctx, shape, pl);
     if (rc != SOCP_OK) return rc;
@@ -354,8 +362,10 @@ int run_solver(socp_ctx *ctx, const socp_shape *shape, long B, const double *d_m
     D.sm_count = ctx->sm_count;
     D.phase_clocks = getenv("SOCP_PHASE_CLOCKS") ? 1 : 0;
     {
-        const char *jm = getenv("SOCP_JAC");               // SOCP_JAC=old: the three-barrier Householder routines (A/B runs)
-        D.jac_fast = !(jm && !strcmp(jm, "old"));
+        // SOCP_JAC=lanes4: the one-barrier, four-lanes-per-column Householder routines (qrfac_w / qform_w; same
+        // bits, measured SLOWER than the thread-per-column ones: 1074 vs 785 ms per step -- kept for A/B runs)
+        const char *jm = getenv("SOCP_JAC");
+        D.jac_fast = (jm && !strcmp(jm, "lanes4")) ? 1 : 0;
     }
     const int grid_int = ctx->sm_count * 8;
     const int grid_adv = ctx->sm_count * 6;
@@ -373,14 +383,15 @@ int run_solver(socp_ctx *ctx, const socp_shape *shape, long B, const double *d_m
         D.time = d_time + first * (D.M + 1);
         D.Xb = d_Xb + first * (D.M + 1) * D.dim;
         const long nthreads = Bw * D.P;
-        solver_init<<<(unsigned)((nthreads + 255) / 256), 256, 0, ctx->stream>>>(D, d_x_in, first);
+        CUDA_TRY(ctx, cudaMemsetAsync(D.counts, 0, 8 * sizeof(int), ctx->stream));
+        solver_init<<<(unsigned)((nthreads + 255) / 256), 256, 0, ctx->stream>>>(D, d_x_in, first, d_active);
         ctx->launches += 1;
         int cur = 0, pending = 0;
         int entering[2] = {(int)Bw, 0};
         // live problems as of the last look at the counters: they only retire, so this bounds the work of
         // every later round; the grids follow it (every kernel strides over its work list, so any grid is
         // correct) and the tail of a solve -- a handful of live problems -- stops launching 1184 idle CTAs
-        long live = Bw;
+        long live = (live_hint >= 0) ? std::min(Bw, std::max<long>(live_hint, 1)) : Bw;
         for (long round = 0; round < max_rounds; ++round) {
             const long items = live * std::max(D.nJ, D.P);                       // upper bound on work items
             const int gi = (int)std::max<long>(1, std::min<long>(grid_int, (items + 127) / 128));
@@ -411,7 +422,7 @@ int run_solver(socp_ctx *ctx, const socp_shape *shape, long B, const double *d_m
             prof_harvest(ctx, pending);
         }
         const long nfin = std::max<long>(nthreads, d_fjac_out ? Bw * (long)D.P * D.P : 0);
-        solver_finish<<<(unsigned)((nfin + 255) / 256), 256, 0, ctx->stream>>>(D, first, d_x_out, d_fvec_out, d_fjac_out, d_info, d_nfev, d_fnorm, d_njev);
+        solver_finish<<<(unsigned)((nfin + 255) / 256), 256, 0, ctx->stream>>>(D, first, d_x_out, d_fvec_out, d_fjac_out, d_info, d_nfev, d_fnorm, d_njev, d_active);
         ctx->launches += 1;
         CUDA_TRY(ctx, cudaGetLastError());
     }
@@ -599,134 +610,116 @@ int socp_traj_var_batch(socp_ctx *ctx, int model_id, int step_nbr, long B, const
     return SOCP_OK;
 }
 
-// ---- continuation (host state machines around socp_solve_batch) ---------------------------------
-// Each problem runs the reference's homotopy loop (shooting.cpp:598-692 / :695-778) with its own
-// b, b_prec; all problems still in their loop are solved together, one batched solve per pass.
+// ---- continuation: per-problem homotopy state machines ON THE DEVICE --------------------------------------------
+// Each problem runs the reference's loop (shooting.cpp:598-692 / :695-778) with its own b, b_prec; all problems
+// still in their loop are solved together, one batched solve per pass.  The state machine, the boundary / parameter
+// data of the next pass and the accepted solutions never leave the device: per pass the host launches four kernels
+// around run_solver and reads one int (problems still active).  SOCP_HOST buffers are staged once before the first
+// pass and fetched once after the last.
+static int run_continuation(socp_ctx *ctx, const socp_shape *shape, long B, double *mparams, const double *time_prec,
+                            const double *Xb_prec, const double *time_des, const double *Xb_des, double *x, double xtol,
+                            int maxfev, double step, double step_min, int param_idx, const double *goal, int *info,
+                            int *calls, int mem) {
+    const int P = socp_num_param(shape), dim = kDim[shape->model_id], np = kNP[shape->model_id], M = shape->num_multi;
+    const int nt = M + 1, nx = (M + 1) * dim;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    int rc = SOCP_OK;
+    // caller arrays on the device (staged copies in HOST mode)
+    double *d_mp = (double *)stage_in(ctx, SLOT_MPARAMS, (const double *)mparams, (size_t)B * np, mem, &rc);
+    const double *d_tp = stage_in(ctx, SLOT_TIME, time_prec, (size_t)B * nt, mem, &rc);
+    const double *d_Xp = stage_in(ctx, SLOT_XB, Xb_prec, (size_t)B * nx, mem, &rc);
+    const double *d_td = stage_in(ctx, SLOT_CONT_A, time_des, (size_t)B * nt, mem, &rc);
+    const double *d_Xd = stage_in(ctx, SLOT_CONT_B, Xb_des, (size_t)B * nx, mem, &rc);
+    const double *d_goal = stage_in(ctx, SLOT_AUX0, goal, (size_t)B, mem, &rc);
+    double *d_x = (double *)stage_in(ctx, SLOT_X, (const double *)x, (size_t)B * P, mem, &rc);
+    int *d_info = stage_out(ctx, SLOT_INFO, info, (size_t)B, mem, &rc);
+    int *d_calls = stage_out(ctx, SLOT_NFEV, calls, (size_t)B * 2, mem, &rc);
+    if (rc != SOCP_OK) return bail(ctx, rc);
+    // homotopy state
+    const bool boundary = param_idx < 0;
+    size_t need = 0;
+    {
+        Carver c(nullptr);
+        c.take<double>(3 * (size_t)B); c.take<double>((size_t)B * P);
+        if (boundary) { c.take<double>((size_t)B * nt); c.take<double>((size_t)B * nx); }
+        c.take<int>(3 * (size_t)B + 8);
+        need = c.off + 512;
+    }
+    void *blob = ws(ctx, SLOT_CONT, need);
+    if (!blob) return bail(ctx, SOCP_ERR_NOMEM);
+    Carver c(blob);
+    ContDev C;
+    memset(&C, 0, sizeof C);
+    C.B = B; C.P = P; C.np = np; C.nt = nt; C.nx = nx; C.param_idx = param_idx; C.step = step; C.step_min = step_min;
+    double *st3 = c.take<double>(3 * (size_t)B);
+    C.b = st3; C.b_prec = st3 + B; C.rstart = st3 + 2 * B;
+    C.xw = c.take<double>((size_t)B * P);
+    if (boundary) { C.time_w = c.take<double>((size_t)B * nt); C.Xb_w = c.take<double>((size_t)B * nx); }
+    int *ints = c.take<int>(3 * (size_t)B + 8);
+    C.active = ints; C.info_w = ints + B; C.nfev_w = ints + 2 * B; C.n_active = ints + 3 * B;
+    C.goal = d_goal; C.x = d_x; C.mparams = d_mp;
+    C.time_prec = d_tp; C.Xb_prec = d_Xp; C.time_des = d_td; C.Xb_des = d_Xd;
+    C.info = d_info; C.calls = d_calls;
+    if (!ctx->solver.h_counts) {
+        CUDA_TRY(ctx, cudaHostAlloc((void **)&ctx->solver.h_counts, 8 * sizeof(int), cudaHostAllocDefault));
+        CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->solver.ev, cudaEventDisableTiming));
+    }
+    const unsigned gP = (unsigned)(((size_t)B * P + 255) / 256);
+    cont_begin<<<gP, 256, 0, ctx->stream>>>(C);
+    ctx->launches += 1;
+    long n_active = B;
+    // the loop ends when no problem is left in its homotopy; every pass retires or advances each active problem,
+    // and a problem needs at most ~ 1/step + 2 log2(1/step_min) passes
+    for (long pass = 0; n_active > 0; ++pass) {
+        const size_t items = boundary ? (size_t)B * (nt + nx) : (size_t)B;
+        cont_setup<<<(unsigned)((items + 255) / 256), 256, 0, ctx->stream>>>(C);
+        ctx->launches += 1;
+        rc = run_solver(ctx, shape, B, d_mp, boundary ? C.time_w : d_tp, boundary ? C.Xb_w : d_Xp, C.xw, RUN_SOLVE, xtol, maxfev,
+                        1e-15, C.xw, nullptr, nullptr, C.info_w, C.nfev_w, nullptr, 0, nullptr, C.active, n_active);
+        if (rc != SOCP_OK) return bail(ctx, rc);
+        cont_update<<<(unsigned)(((size_t)B * 32 + 255) / 256), 256, 0, ctx->stream>>>(C);
+        ctx->launches += 1;
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->solver.h_counts + 4, C.n_active, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        n_active = ctx->solver.h_counts[4];
+    }
+    CUDA_TRY(ctx, cudaGetLastError());
+    if ((rc = fetch_out(ctx, x, (const double *)d_x, (size_t)B * P, mem)) != SOCP_OK) return bail(ctx, rc);
+    if (!boundary && (rc = fetch_out(ctx, mparams, (const double *)d_mp, (size_t)B * np, mem)) != SOCP_OK) return bail(ctx, rc);
+    if ((rc = fetch_out(ctx, info, (const int *)d_info, (size_t)B, mem)) != SOCP_OK) return bail(ctx, rc);
+    if ((rc = fetch_out(ctx, calls, (const int *)d_calls, (size_t)B * 2, mem)) != SOCP_OK) return bail(ctx, rc);
+    if (mem == SOCP_HOST) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return SOCP_OK;
+}
 
 int socp_continuation_param_batch(socp_ctx *ctx, const socp_shape *shape, long B, double *mparams,
                                   const double *time, const double *Xb, double *x, double xtol,
                                   int maxfev, double step, int param_idx, const double *goal,
-                                  double step_min, int *info, int *calls) {
+                                  double step_min, int *info, int *calls, int mem) {
     int rc = check_problem_args(ctx, shape, B, mparams, time, Xb, x, info);
-    if (rc != SOCP_OK) return bail(ctx, rc);
-    const int P = socp_num_param(shape), dim = kDim[shape->model_id], np = kNP[shape->model_id], M = shape->num_multi;
+    if (rc != SOCP_OK) return rc;
+    const int np = kNP[shape->model_id];
     if (param_idx < 0 || param_idx >= np || !goal) return fail(ctx, SOCP_ERR_ARG, "bad parameter index / goal");
+    if (xtol < 0. || maxfev <= 0) return fail(ctx, SOCP_ERR_ARG, "xtol < 0 or maxfev <= 0");
     if (step <= 0) step = 1.0;                              // shooting.cpp:352-355
-    std::vector<double> Rstart(B), b(B), b_prec(B, 0.0), tmp((size_t)B * P);
-    std::vector<char> active(B, 1);
-    for (long k = 0; k < B; ++k) {
-        Rstart[k] = mparams[k * np + param_idx];
-        b[k] = std::min(step, 1.0);
-        mparams[k * np + param_idx] = (1 - b[k]) * Rstart[k] + b[k] * goal[k];
-        info[k] = 0;
-        if (calls) { calls[2 * k] = 0; calls[2 * k + 1] = 0; }
-    }
-    memcpy(tmp.data(), x, sizeof(double) * (size_t)B * P);
-    std::vector<long> idx;
-    std::vector<double> wx, wmp, wtime, wXb, wfn;
-    std::vector<int> winfo, wnfev;
-    for (;;) {
-        idx.clear();
-        for (long k = 0; k < B; ++k) if (active[k]) idx.push_back(k);
-        if (idx.empty()) break;
-        const long A = (long)idx.size();
-        wx.resize((size_t)A * P); wmp.resize((size_t)A * np); wtime.resize((size_t)A * (M + 1)); wXb.resize((size_t)A * (M + 1) * dim);
-        winfo.resize(A); wnfev.resize(A); wfn.resize(A);
-        for (long a = 0; a < A; ++a) {
-            const long k = idx[a];
-            memcpy(&wx[a * P], &tmp[k * P], sizeof(double) * P);
-            memcpy(&wmp[a * np], &mparams[k * np], sizeof(double) * np);
-            memcpy(&wtime[a * (M + 1)], &time[k * (M + 1)], sizeof(double) * (M + 1));
-            memcpy(&wXb[a * (M + 1) * dim], &Xb[k * (M + 1) * dim], sizeof(double) * (M + 1) * dim);
-        }
-        rc = socp_solve_batch(ctx, shape, A, wmp.data(), wtime.data(), wXb.data(), wx.data(), xtol, maxfev,
-                              winfo.data(), wnfev.data(), wfn.data(), SOCP_HOST);
-        if (rc != SOCP_OK) return bail(ctx, rc);
-        for (long a = 0; a < A; ++a) {
-            const long k = idx[a];
-            const int ret = winfo[a];
-            info[k] = ret;
-            if (calls) { calls[2 * k] += 1; calls[2 * k + 1] += wnfev[a]; }
-            if (ret != 1) {
-                if (fabs(b[k] - b_prec[k]) < step_min) active[k] = 0;
-                b[k] = b_prec[k] + (b[k] - b_prec[k]) / 2;
-                memcpy(&tmp[k * P], &x[k * P], sizeof(double) * P);
-                mparams[k * np + param_idx] = (1 - b[k]) * Rstart[k] + b[k] * goal[k];
-            } else {
-                memcpy(&tmp[k * P], &wx[a * P], sizeof(double) * P);
-                if (b[k] == 1) {
-                    active[k] = 0;
-                    memcpy(&x[k * P], &tmp[k * P], sizeof(double) * P);
-                } else {
-                    b_prec[k] = b[k];
-                    b[k] = std::min(b[k] + step, 1.0);
-                    memcpy(&x[k * P], &tmp[k * P], sizeof(double) * P);
-                    mparams[k * np + param_idx] = (1 - b[k]) * Rstart[k] + b[k] * goal[k];
-                }
-            }
-        }
-    }
-    return SOCP_OK;
+    if (B == 0) return SOCP_OK;
+    return run_continuation(ctx, shape, B, mparams, time, Xb, nullptr, nullptr, x, xtol, maxfev, step, step_min, param_idx,
+                            goal, info, calls, mem);
 }
 
 int socp_continuation_boundary_batch(socp_ctx *ctx, const socp_shape *shape, long B,
                                      const double *mparams, const double *time_prec,
                                      const double *Xb_prec, const double *time_des,
                                      const double *Xb_des, double *x, double xtol, int maxfev,
-                                     double step, double step_min, int *info, int *calls) {
+                                     double step, double step_min, int *info, int *calls, int mem) {
     int rc = check_problem_args(ctx, shape, B, mparams, time_prec, Xb_prec, x, info);
-    if (rc != SOCP_OK) return bail(ctx, rc);
+    if (rc != SOCP_OK) return rc;
     if (!time_des || !Xb_des) return fail(ctx, SOCP_ERR_ARG, "NULL desired boundary data");
-    const int P = socp_num_param(shape), dim = kDim[shape->model_id], np = kNP[shape->model_id], M = shape->num_multi;
-    const int nt = M + 1, nx = (M + 1) * dim;
+    if (xtol < 0. || maxfev <= 0) return fail(ctx, SOCP_ERR_ARG, "xtol < 0 or maxfev <= 0");
     if (step <= 0) return fail(ctx, SOCP_ERR_ARG, "continuation step must be > 0 (use socp_solve_batch otherwise)");
-    std::vector<double> b(B), b_prec(B, 0.0), tmp((size_t)B * P);
-    std::vector<char> active(B, 1);
-    for (long k = 0; k < B; ++k) {
-        b[k] = std::min(step, 1.0);
-        info[k] = 0;
-        if (calls) { calls[2 * k] = 0; calls[2 * k + 1] = 0; }
-    }
-    memcpy(tmp.data(), x, sizeof(double) * (size_t)B * P);
-    std::vector<long> idx;
-    std::vector<double> wx, wmp, wtime, wXb, wfn;
-    std::vector<int> winfo, wnfev;
-    for (;;) {
-        idx.clear();
-        for (long k = 0; k < B; ++k) if (active[k]) idx.push_back(k);
-        if (idx.empty()) break;
-        const long A = (long)idx.size();
-        wx.resize((size_t)A * P); wmp.resize((size_t)A * np); wtime.resize((size_t)A * nt); wXb.resize((size_t)A * nx);
-        winfo.resize(A); wnfev.resize(A); wfn.resize(A);
-        for (long a = 0; a < A; ++a) {
-            const long k = idx[a];
-            const double bk = b[k];
-            memcpy(&wx[a * P], &tmp[k * P], sizeof(double) * P);
-            memcpy(&wmp[a * np], &mparams[k * np], sizeof(double) * np);
-            for (int i = 0; i < nt; ++i) wtime[a * nt + i] = (1 - bk) * time_prec[k * nt + i] + bk * time_des[k * nt + i];
-            for (int i = 0; i < nx; ++i) wXb[a * nx + i] = (1 - bk) * Xb_prec[k * nx + i] + bk * Xb_des[k * nx + i];
-        }
-        rc = socp_solve_batch(ctx, shape, A, wmp.data(), wtime.data(), wXb.data(), wx.data(), xtol, maxfev,
-                              winfo.data(), wnfev.data(), wfn.data(), SOCP_HOST);
-        if (rc != SOCP_OK) return bail(ctx, rc);
-        for (long a = 0; a < A; ++a) {
-            const long k = idx[a];
-            const int ret = winfo[a];
-            info[k] = ret;
-            if (calls) { calls[2 * k] += 1; calls[2 * k + 1] += wnfev[a]; }
-            if (ret != 1) {
-                if (fabs(b[k] - b_prec[k]) < step_min) active[k] = 0;
-                b[k] = b_prec[k] + (b[k] - b_prec[k]) / 2;
-                memcpy(&tmp[k * P], &x[k * P], sizeof(double) * P);
-            } else {
-                memcpy(&tmp[k * P], &wx[a * P], sizeof(double) * P);
-                memcpy(&x[k * P], &tmp[k * P], sizeof(double) * P);
-                if (b[k] == 1) active[k] = 0;
-                else { b_prec[k] = b[k]; b[k] = std::min(b[k] + step, 1.0); }
-            }
-        }
-    }
-    return SOCP_OK;
+    if (B == 0) return SOCP_OK;
+    return run_continuation(ctx, shape, B, (double *)mparams, time_prec, Xb_prec, time_des, Xb_des, x, xtol, maxfev, step,
+                            step_min, -1, nullptr, info, calls, mem);
 }
 
 }  // extern "C"

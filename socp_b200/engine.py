@@ -372,31 +372,48 @@ class Engine:
         return dict(x=x, info=info, nfev=nfev, njev=njev, fnorm=fnorm)
 
     def continuation_param_batch(self, shape, mparams, time, Xb, x, step, param_idx, goal, xtol=1e-8,
-                                 maxfev=10000, step_min=1e-12):
-        """shooting::SolveShootingContinuation(step, Rdata, Rgoal) for B problems (host arrays)."""
+                                 maxfev=10000, step_min=1e-12, info=None, calls=None):
+        """shooting::SolveShootingContinuation(step, Rdata, Rgoal) for B problems.
+        Host arrays: works on copies, returns dict(x, info, calls, mparams).  Torch CUDA tensors: x and mparams are
+        updated IN PLACE on the device (goal, info, calls are device tensors too; info/calls are created when None)
+        and no problem data crosses PCIe."""
         B = x.shape[0]
-        mparams = np.ascontiguousarray(self._bcast_params(mparams, B, model_nparams(shape.model_id))).copy()
-        x = np.ascontiguousarray(x, dtype=np.float64).copy()
-        goal = np.ascontiguousarray(np.broadcast_to(np.asarray(goal, dtype=np.float64), (B,)))
-        info = np.empty(B, dtype=np.int32)
-        calls = np.empty((B, 2), dtype=np.int32)
-        a = _Arg(HOST)
+        mem = self._mem(x)
+        if mem == HOST:
+            mparams = np.ascontiguousarray(self._bcast_params(mparams, B, model_nparams(shape.model_id))).copy()
+            x = np.ascontiguousarray(x, dtype=np.float64).copy()
+            goal = np.ascontiguousarray(np.broadcast_to(np.asarray(goal, dtype=np.float64), (B,)))
+            info = np.empty(B, dtype=np.int32)
+            calls = np.empty((B, 2), dtype=np.int32)
+        else:
+            import torch
+            info = torch.empty(B, dtype=torch.int32, device=x.device) if info is None else info
+            calls = torch.empty((B, 2), dtype=torch.int32, device=x.device) if calls is None else calls
+        a = self._arg(mem)
         self._check(self._L.socp_continuation_param_batch(
             self._h, ctypes.byref(shape), B, a.out(mparams), a.inp(time), a.inp(Xb), a.out(x), float(xtol),
-            int(maxfev), float(step), int(param_idx), a.inp(goal), float(step_min), a.out(info, np.int32), a.out(calls, np.int32)))
+            int(maxfev), float(step), int(param_idx), a.inp(goal), float(step_min), a.out(info, np.int32),
+            a.out(calls, np.int32), mem))
         return dict(x=x, info=info, calls=calls, mparams=mparams)
 
     def continuation_boundary_batch(self, shape, mparams, time_prec, Xb_prec, time_des, Xb_des, x, step,
-                                    xtol=1e-8, maxfev=10000, step_min=1e-12):
-        """shooting::SolveShootingContinuation(step) on the boundary data for B problems."""
+                                    xtol=1e-8, maxfev=10000, step_min=1e-12, info=None, calls=None):
+        """shooting::SolveShootingContinuation(step) on the boundary data for B problems (host arrays: works on a
+        copy of x; torch CUDA tensors: x updated in place on the device)."""
         B = x.shape[0]
-        mparams = self._bcast_params(mparams, B, model_nparams(shape.model_id))
-        x = np.ascontiguousarray(x, dtype=np.float64).copy()
-        info = np.empty(B, dtype=np.int32)
-        calls = np.empty((B, 2), dtype=np.int32)
-        a = _Arg(HOST)
+        mem = self._mem(x)
+        if mem == HOST:
+            mparams = self._bcast_params(mparams, B, model_nparams(shape.model_id))
+            x = np.ascontiguousarray(x, dtype=np.float64).copy()
+            info = np.empty(B, dtype=np.int32)
+            calls = np.empty((B, 2), dtype=np.int32)
+        else:
+            import torch
+            info = torch.empty(B, dtype=torch.int32, device=x.device) if info is None else info
+            calls = torch.empty((B, 2), dtype=torch.int32, device=x.device) if calls is None else calls
+        a = self._arg(mem)
         self._check(self._L.socp_continuation_boundary_batch(
             self._h, ctypes.byref(shape), B, a.inp(mparams), a.inp(time_prec), a.inp(Xb_prec),
             a.inp(time_des), a.inp(Xb_des), a.out(x), float(xtol), int(maxfev), float(step),
-            float(step_min), a.out(info, np.int32), a.out(calls, np.int32)))
+            float(step_min), a.out(info, np.int32), a.out(calls, np.int32), mem))
         return dict(x=x, info=info, calls=calls)
