@@ -68,11 +68,16 @@ def parse():
 class Workload:
     """Arrays of one batch as the C ABI takes them + what the CPU checkers need to rebuild problem k."""
 
-    def __init__(self, name, model, shape, mp, time_, Xb, x0, xtol, steps, flops_key, label, mode_t, mode_X, M):
+    def __init__(self, name, model, shape, mp, time_, Xb, x0, xtol, steps, flops_key, label, mode_t, mode_X, M,
+                 kind="solve", cont=None, ode_tol=0.0):
         self.name, self.model, self.shape = name, model, shape
         self.mp, self.time, self.Xb, self.x0 = mp, time_, Xb, x0
         self.xtol, self.steps, self.flops_key, self.label = xtol, steps, flops_key, label
         self.mode_t, self.mode_X, self.M = mode_t, mode_X, M
+        # kind: "solve" (one root solve per problem), "cont_boundary" (homotopy on the boundary data: cont = dict(step,
+        # time_des[B][M+1], Xb_des[B][(M+1) dim])), "cont_param" (homotopy on a model parameter: cont = dict(step, pname, goal[B]))
+        self.kind, self.cont, self.ode_tol = kind, cont, ode_tol
+        self.unit = "solves/s" if kind == "solve" else "homotopies/s"
 
     @property
     def B(self):
@@ -86,10 +91,18 @@ class Workload:
         """Problem k as a scenario spec for the CPU checkers (tests/scenarios.py)."""
         import scenarios as S
         n = S.DIM[self.model]
-        return S.make_spec(self.model, self.M, self.mode_t, self.mode_X, self.time[k], self.Xb[k].reshape(self.M + 1, n),
-                           self.x0[k] if x0 is None else x0, self.xtol,
-                           mparams=self.mp[k] if mparams is None else mparams, steps=self.steps,
-                           name="%s_%d" % (self.name, k))
+        sp = S.make_spec(self.model, self.M, self.mode_t, self.mode_X, self.time[k], self.Xb[k].reshape(self.M + 1, n),
+                         self.x0[k] if x0 is None else x0, self.xtol,
+                         mparams=self.mp[k] if mparams is None else mparams, steps=self.steps,
+                         name="%s_%d" % (self.name, k))
+        if self.ode_tol > 0:
+            sp["ode_tol"] = self.ode_tol
+        if self.kind == "cont_boundary":
+            sp["cont"] = dict(step=self.cont["step"], timed=[float(v) for v in self.cont["time_des"][k]],
+                              Xd=[[float(v) for v in r] for r in self.cont["Xb_des"][k].reshape(self.M + 1, n)])
+        elif self.kind == "cont_param":
+            sp["cont"] = dict(step=self.cont["step"], pname=self.cont["pname"], goal=float(self.cont["goal"][k]))
+        return sp
 
 
 def goddard_workload(eng, B, seed):
@@ -154,7 +167,84 @@ def wl_goddard_warm(eng, B, seed):
     return w
 
 
-WORKLOADS = {"goddard": (wl_goddard, 100000), "goddard_warm": (wl_goddard_warm, 100000)}
+def _golden_spec(kind, name):
+    import golden_util as G
+    e = G.by_name(kind, name)
+    return e, G.spec_from_hex(e["spec"])
+
+
+def wl_interceptor(eng, B, seed):
+    """BASELINE configs[2] / SURVEY C3: interceptor guidance shooting (P = 13).  Every problem is the boundary
+    continuation of tests/testInterceptor.cpp:137-139 (step 0.1: eleven solves) from the solved initialisation
+    problem (`initState`, :152-199, mu_gft 0 -> 1; shared by all problems, recorded from oracle/_ref in
+    tests/golden/golden.json) to scenario S3 (:84-97) with a perturbed target: altitude +-500 m, heading +-0.05 rad,
+    latitude / longitude +-2 km."""
+    import socp_b200 as sb
+    import scenarios as S
+    import golden_util as G
+    e, spec = _golden_spec("cont_boundary", "interceptor_S3")
+    timed, Xd0 = np.asarray(G.unhex(e["timed"])), np.asarray(G.unhex(e["Xd"]))
+    rng = np.random.default_rng(seed)
+    Xd = np.tile(Xd0.reshape(1, 2, 6), (B, 1, 1))
+    Xd[:, 1, 0] += rng.uniform(-500, 500, B)
+    Xd[:, 1, 3] += rng.uniform(-0.05, 0.05, B)
+    Xd[:, 1, 4] += rng.uniform(-2000, 2000, B) / S.R_EARTH
+    Xd[:, 1, 5] += rng.uniform(-2000, 2000, B) / S.R_EARTH
+    shape = sb.make_shape(sb.INTERCEPTOR, 1, spec["mode_t"], spec["mode_X"], spec["steps"])
+    return Workload("interceptor", S.INTERCEPTOR, shape, np.tile(np.array(spec["mparams"]), (B, 1)),
+                    np.tile(np.array(spec["time"]), (B, 1)), np.tile(np.array(spec["Xb"]).reshape(1, -1), (B, 1)),
+                    np.tile(np.array(spec["x0"]), (B, 1)), spec["xtol"], spec["steps"], "interceptor",
+                    "interceptor_S3_boundary_continuation_P13_batch (BASELINE configs[2], SURVEY C3: 11 solves per problem)",
+                    spec["mode_t"], spec["mode_X"], 1, kind="cont_boundary",
+                    cont=dict(step=0.1, time_des=np.tile(timed, (B, 1)), Xb_des=Xd.reshape(B, -1)))
+
+
+def wl_covid19(eng, B, seed):
+    """BASELINE configs[4] / SURVEY C5: Covid-19 SEIR control (M = 20 segments x 1000 RK4 steps, P = 160), a
+    continuation sweep over the cost weight of the ICU constraint: every problem starts from the reference's
+    solution of tests/testCovid19.cpp:42-93 (muI = 1; recorded from oracle/_ref) and runs the parameter homotopy
+    of shooting.cpp:695-778 on muI to its own goal, log-uniform in [0.1, 10], step 0.5."""
+    import socp_b200 as sb
+    import scenarios as S
+    import golden_util as G
+    e, spec = _golden_spec("solve", "covid_stage1")
+    assert e["info"] == 1
+    xs = np.asarray(G.unhex(e["x"]))
+    rng = np.random.default_rng(seed)
+    goal = np.exp(rng.uniform(np.log(0.1), np.log(10.0), B))
+    shape = sb.make_shape(sb.COVID19, 20, spec["mode_t"], spec["mode_X"], spec["steps"])
+    return Workload("covid19", S.COVID19, shape, np.tile(np.array(spec["mparams"]), (B, 1)),
+                    np.tile(np.array(spec["time"]), (B, 1)), np.tile(np.array(spec["Xb"]).reshape(1, -1), (B, 1)),
+                    np.tile(xs, (B, 1)), spec["xtol"], spec["steps"], "covid19",
+                    "covid19_muI_continuation_sweep_M20_P160_batch (BASELINE configs[4], SURVEY C5)",
+                    spec["mode_t"], spec["mode_X"], 20, kind="cont_param", cont=dict(step=0.5, pname="muI", goal=goal))
+
+
+def wl_vtol_rk45(eng, B, seed):
+    """BASELINE configs[3] / SURVEY C4: vtolUAV with the obstacle map of data/vtolUAV, adaptive Dormand-Prince
+    segments (the reference's -D_USE_BOOST build: xtol 1e-4, odeIntTol 1e-5, tests/testVtolUAV.cpp:65-66): the first
+    leg of the waypoint path (:163-214, WP0 -> WP1, free final time) with the start point jittered by +-0.5 m."""
+    import socp_b200 as sb
+    import scenarios as S
+    o = S.VTOL_OBSTACLES
+    if eng is not None:
+        eng.set_obstacles(o["type"], o["pos"], o["rad"])
+    v = S.vtol_first_problem()
+    rng = np.random.default_rng(seed)
+    jit = rng.uniform(-0.5, 0.5, (B, 3))
+    Xb = np.tile(np.array(v["Xb"]).reshape(1, -1), (B, 1))
+    x0 = np.tile(np.array(v["x0"]), (B, 1))
+    Xb[:, 0:3] += jit
+    x0[:, 0:3] += jit
+    shape = sb.make_shape(sb.VTOL_UAV, 1, v["mode_t"], v["mode_X"], v["steps"], ode_tol=1e-5)
+    return Workload("vtol_rk45", S.VTOL, shape, np.tile(np.array(v["mparams"]), (B, 1)), np.tile(np.array(v["time"]), (B, 1)),
+                    Xb, x0, v["xtol"], v["steps"], "vtol",
+                    "vtolUAV_first_leg_dopri5_P13_batch (BASELINE configs[3], SURVEY C4: adaptive RK45, odeIntTol 1e-5)",
+                    v["mode_t"], v["mode_X"], 1, ode_tol=1e-5)
+
+
+WORKLOADS = {"goddard": (wl_goddard, 100000), "goddard_warm": (wl_goddard_warm, 100000),
+             "interceptor": (wl_interceptor, 1000000), "covid19": (wl_covid19, 4096), "vtol_rk45": (wl_vtol_rk45, 1000000)}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -174,7 +264,27 @@ def _cpu_worker(job):
     be = _cpu_backend()
     out = []
     for s in specs:
-        if kind == "solve":
+        if kind == "run":
+            # whatever the workload's unit of work is; (info, nfev or nfev_total, x, solver calls)
+            if s.get("ode_tol"):
+                # adaptive Dormand-Prince: the reference needs Boost.Odeint for it (absent): the C port stands in
+                import backends
+                p = backends.OracleBackend().problem(s)
+                p.p.integrator, p.p.ode_tol = 1, s["ode_tol"]
+                q = p.solve(s["x0"], xtol=s["xtol"])
+                out.append((int(q["info"]), int(q["nfev"]), np.asarray(q["x"], dtype=np.float64), 1))
+            elif "cont" in s and "timed" in s["cont"]:
+                c = s["cont"]
+                r = be.continuation_boundary(s, c["step"], np.asarray(c["timed"]), np.asarray(c["Xd"]))
+                out.append((int(r["info"]), int(r["nfev_total"]), np.asarray(r["x"], dtype=np.float64), int(r["solver_calls"])))
+            elif "cont" in s:
+                c = s["cont"]
+                r = be.continuation_param(s, c["step"], c["pname"], c["goal"])
+                out.append((int(r["info"]), int(r["nfev_total"]), np.asarray(r["x"], dtype=np.float64), int(r["solver_calls"])))
+            else:
+                r = be.solve(s)
+                out.append((int(r["info"]), int(r["nfev"]), np.asarray(r["x"], dtype=np.float64), 1))
+        elif kind == "solve":
             r = be.solve(s)
             out.append((int(r["info"]), int(r["nfev"]), np.asarray(r["x"], dtype=np.float64)))
         elif kind == "cont_param":
@@ -220,6 +330,10 @@ class CpuPool:
     def solve(self, specs):
         dt, res = self.run("solve", specs)
         return dt, res
+
+    def work(self, specs):
+        """One unit of work of the workload per spec (a solve or a whole homotopy): [(info, nfev, x, solver calls)]."""
+        return self.run("run", specs)
 
     def close(self):
         self.pool.close()
@@ -350,44 +464,58 @@ def run_reference(args, rank):
     n = per_step * (args.steps + args.warmup)
     batch = args.batch or WORKLOADS[args.workload][1]
     # build the same problems as the GPU arm (same seed); the guess integration runs on the CPU port
-    ora = OracleBackend()
-    Xi, xf0 = S.goddard_batch_inputs(batch, seed=20260002)
-    xstar = reference_xstar() if args.workload == "goddard_warm" else None
-    specs = []
-    for k in range(n):
-        kk = k % batch
-        s = S.goddard_problem(lambda mp, a, b, c: ora.traj(S.GODDARD, mp, a, b, c, 10), Xi=Xi[kk], xf0=xf0[kk])
-        if xstar is not None:
-            s["x0"] = [float(v) for v in xstar]
-        specs.append(s)
-    for w in range(args.warmup):
-        pool.solve(specs[w * per_step:(w + 1) * per_step])
+    if args.workload in ("goddard", "goddard_warm"):
+        ora = OracleBackend()
+        Xi, xf0 = S.goddard_batch_inputs(batch, seed=20260002)
+        xstar = reference_xstar() if args.workload == "goddard_warm" else None
+        specs = []
+        for k in range(n):
+            kk = k % batch
+            s = S.goddard_problem(lambda mp, a, b, c: ora.traj(S.GODDARD, mp, a, b, c, 10), Xi=Xi[kk], xf0=xf0[kk])
+            if xstar is not None:
+                s["x0"] = [float(v) for v in xstar]
+            specs.append(s)
+        unit, steps_per_nfev = "solves/s", 60.0
+    else:
+        w = WORKLOADS[args.workload][0](None, min(n, batch), 20260002)
+        specs = [w.spec(k % w.B) for k in range(n)]
+        unit, steps_per_nfev = w.unit, float(w.M * w.steps)
+    for wu in range(args.warmup):
+        pool.work(specs[wu * per_step:(wu + 1) * per_step])
     t_total, res = 0.0, []
-    for s in range(args.steps):
-        lo = (args.warmup + s) * per_step
-        dt, r = pool.solve(specs[lo:lo + per_step])
+    for st in range(args.steps):
+        lo = (args.warmup + st) * per_step
+        dt, r = pool.work(specs[lo:lo + per_step])
         t_total += dt
         res += r
     pool.close()
     value = per_step * args.steps / t_total
     nfev = sum(r[1] for r in res)
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": args.gpus,
+        "impl": "reference", "metric": METRIC if args.workload.startswith("goddard") else "shooting %s (%s)" % (unit.replace("/s", "/sec"), WORKLOAD_LABELS[args.workload]),
+        "value": value, "unit": unit, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps,
         "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD_LABELS.get(args.workload, args.workload), "batch_per_gpu": batch,
                    "sample_per_step": per_step},
-        "rk4_steps_per_s": nfev * 60.0 / t_total,
+        "rk4_steps_per_s": nfev * steps_per_nfev / t_total,
         "converged_fraction": sum(1 for r in res if r[0] == 1) / len(res),
-        "cpu_baseline": {"value": value, "unit": "solves/s", "cores": pool.cores, "kind": pool.kind,
+        "cpu_baseline": {"value": value, "unit": unit, "cores": pool.cores,
+                         "kind": "port" if args.workload == "vtol_rk45" else pool.kind,
                          "sample": "%d problems of the batch per step, one process per core" % per_step},
-        "e2e": {"value": value, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
 
 
+# the CPU side of the heavier workloads is bounded to ~10-30 s of host work
+PARITY_CAP = {"covid19": 32, "interceptor": 1024, "vtol_rk45": 1024}
+
 WORKLOAD_LABELS = {
+    "interceptor": "interceptor_S3_boundary_continuation_P13_batch (configs[2])",
+    "covid19": "covid19_muI_continuation_sweep_M20_P160_batch (configs[4])",
+    "vtol_rk45": "vtolUAV_first_leg_dopri5_P13_batch (configs[3])",
     "goddard": "goddard_free_tf_M6_P85_batch (configs[1])",
     "goddard_warm": "goddard_warm_start_M6_P85_batch (SURVEY C2 stage 2)",
 }
@@ -401,12 +529,45 @@ def la_flops_per_iteration(P):
     return 25.0 * P * P
 
 
+def device_arrays(torch, dev, w):
+    def dv(a):
+        return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    d = dict(mp=dv(w.mp), time=dv(w.time), Xb=dv(w.Xb), x0=dv(w.x0))
+    d["x"] = torch.empty_like(d["x0"])
+    d["info"] = torch.empty(w.B, dtype=torch.int32, device=dev)
+    d["nfev"] = torch.empty(w.B, dtype=torch.int32, device=dev)
+    d["fnorm"] = torch.empty(w.B, dtype=torch.float64, device=dev)
+    if w.kind != "solve":
+        d["calls"] = torch.empty((w.B, 2), dtype=torch.int32, device=dev)
+    if w.kind == "cont_boundary":
+        d["time_des"], d["Xb_des"] = dv(w.cont["time_des"]), dv(w.cont["Xb_des"])
+    if w.kind == "cont_param":
+        d["goal"], d["mpw"] = dv(w.cont["goal"]), torch.empty_like(d["mp"])
+    return d
+
+
+def unit_of_work(eng, w, a, x, mp=None, info=None, nfev=None, fnorm=None, calls=None):
+    """One unit of work of the workload for every problem through the public API: a root solve, or a whole
+    homotopy.  `a` holds host (numpy) or device (torch) arrays; x is updated in place."""
+    import scenarios as S
+    if w.kind == "solve":
+        return eng.solve_batch(w.shape, a["mp"], a["time"], a["Xb"], x, xtol=w.xtol, maxfev=10000, info=info, nfev=nfev, fnorm=fnorm)
+    if w.kind == "cont_boundary":
+        return eng.continuation_boundary_batch(w.shape, a["mp"], a["time"], a["Xb"], a["time_des"], a["Xb_des"], x, w.cont["step"],
+                                               xtol=w.xtol, info=info, calls=calls)
+    return eng.continuation_param_batch(w.shape, mp, a["time"], a["Xb"], x, w.cont["step"], S.pidx(w.model, w.cont["pname"]),
+                                        a["goal"], xtol=w.xtol, info=info, calls=calls)
+
+
 def timed_solves(eng, torch, dist, world, dev, w, d, steps, warmup, gather):
-    """`warmup` untimed + `steps` timed batched solves, device resident; returns ms for the timed steps."""
+    """`warmup` untimed + `steps` timed units of work for the whole batch, device resident; returns ms for the timed steps."""
     def step():
         d["x"].copy_(d["x0"])
-        eng.solve_batch(w.shape, d["mp"], d["time"], d["Xb"], d["x"], xtol=w.xtol, maxfev=10000, info=d["info"],
-                        nfev=d["nfev"], fnorm=d["fnorm"])
+        if w.kind == "cont_param":
+            d["mpw"].copy_(d["mp"])                      # the homotopy rewrites its parameter in place
+        unit_of_work(eng, w, d, d["x"], mp=d.get("mpw"), info=d["info"], nfev=d["nfev"], fnorm=d["fnorm"], calls=d.get("calls"))
+        if w.kind != "solve":
+            d["nfev"].copy_(d["calls"][:, 1])
         if gather and world > 1:
             # the only exchange of the path: gather converged unknowns + status over NVLink
             from socp_b200 import sharding
@@ -430,23 +591,18 @@ def timed_solves(eng, torch, dist, world, dev, w, d, steps, warmup, gather):
     return e0.elapsed_time(e1), step
 
 
-def device_arrays(torch, dev, w):
-    def dv(a):
-        return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
-    d = dict(mp=dv(w.mp), time=dv(w.time), Xb=dv(w.Xb), x0=dv(w.x0))
-    d["x"] = torch.empty_like(d["x0"])
-    d["info"] = torch.empty(w.B, dtype=torch.int32, device=dev)
-    d["nfev"] = torch.empty(w.B, dtype=torch.int32, device=dev)
-    d["fnorm"] = torch.empty(w.B, dtype=torch.float64, device=dev)
-    return d
-
-
 def e2e_solves(eng, torch, dist, world, dev, w, steps):
-    """The same solves through socp_solve_batch(mem=SOCP_HOST): pinned host buffers, H2D and D2H inside the
+    """The same work through the C ABI with HOST buffers (mem = SOCP_HOST): pinned host memory, H2D and D2H inside the
     timed region (wall clock around the calls, max over ranks)."""
-    h = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in
-         dict(mp=w.mp, time=w.time, Xb=w.Xb, x0=w.x0).items()}
+    src = dict(mp=w.mp, time=w.time, Xb=w.Xb, x0=w.x0)
+    if w.kind == "cont_boundary":
+        src.update(time_des=w.cont["time_des"], Xb_des=w.cont["Xb_des"])
+    if w.kind == "cont_param":
+        src.update(goal=w.cont["goal"])
+    h = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in src.items()}
+    hn = {k: v.numpy() for k, v in h.items()}
     hx = torch.empty_like(h["x0"]).pin_memory()
+    hmp = torch.empty_like(h["mp"]).pin_memory()
     h_info = torch.empty(w.B, dtype=torch.int32).pin_memory()
     h_nfev = torch.empty(w.B, dtype=torch.int32).pin_memory()
     h_fn = torch.empty(w.B, dtype=torch.float64).pin_memory()
@@ -455,21 +611,25 @@ def e2e_solves(eng, torch, dist, world, dev, w, steps):
     t0 = time.perf_counter()
     for _ in range(steps):
         hx.copy_(h["x0"])
-        eng.solve_batch(w.shape, h["mp"].numpy(), h["time"].numpy(), h["Xb"].numpy(), hx.numpy(), xtol=w.xtol,
-                        maxfev=10000, info=h_info.numpy(), nfev=h_nfev.numpy(), fnorm=h_fn.numpy())
+        if w.kind == "solve":
+            unit_of_work(eng, w, hn, hx.numpy(), info=h_info.numpy(), nfev=h_nfev.numpy(), fnorm=h_fn.numpy())
+        else:
+            hmp.copy_(h["mp"])
+            unit_of_work(eng, w, hn, hx.numpy(), mp=hmp.numpy())     # the host form returns fresh result arrays
     dt = time.perf_counter() - t0
     tt = torch.tensor([dt], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     dt = float(tt.item())
-    h2d = (w.mp.nbytes + w.time.nbytes + w.Xb.nbytes + w.x0.nbytes)
+    h2d = sum(v.nbytes for v in src.values())
     d2h = (w.x0.nbytes + 4 * w.B + 4 * w.B + 8 * w.B)
-    return {"value": world * w.B * steps / dt, "unit": "solves/s", "h2d_bytes_per_step": h2d,
+    return {"value": world * w.B * steps / dt, "unit": w.unit, "h2d_bytes_per_step": h2d,
             "d2h_bytes_per_step": d2h, "steps": steps,
-            "api": "socp_solve_batch(mem=SOCP_HOST) via socp_b200.Engine.solve_batch, pinned host buffers"}
+            "api": {"solve": "socp_solve_batch", "cont_boundary": "socp_continuation_boundary_batch",
+                    "cont_param": "socp_continuation_param_batch"}[w.kind] + "(mem=SOCP_HOST) via socp_b200.Engine, pinned host buffers"}
 
 
-def kernel_rooflines(st, ms_profiled, P, flops_step, peak_tf, hbm_peak, traffic):
+def kernel_rooflines(st, ms_profiled, P, flops_step, peak_tf, hbm_peak, traffic, N=14, M=6):
     """Per kernel of the solver round: CUDA-event time of the profiled pass, algorithmic work from the device
     counters, and the roofline that bounds it."""
     LR = P * (P + 1) // 2
@@ -506,9 +666,10 @@ def kernel_rooflines(st, ms_profiled, P, flops_step, peak_tf, hbm_peak, traffic)
         "Jacobian factorisation (Householder QR + accumulation of Q, dense count)")
     # assembly: per Jacobian request the segment end points in (nJ + M records of N + 2 doubles), P columns of
     # at most 2N + 1 reachable rows out, plus the zero fill of the P x P matrix; per residual M records in, P out
-    N = 14
-    bytes_asm_jac = 8.0 * ((90 + 6) * (N + 2) + P * (2 * N + 1) + P * P + 2 * P)
-    bytes_asm_res = 8.0 * (6 * (N + 2) + 2 * P)
+    nfree = P - N * M
+    nJ = N * M + nfree * M                       # perturbed segment integrations of one forward-difference Jacobian
+    bytes_asm_jac = 8.0 * ((nJ + M) * (N + 2) + P * (2 * N + 1) + P * P + 2 * P)
+    bytes_asm_res = 8.0 * (M * (N + 2) + 2 * P)
     add("assemble_kernel(+zero_fjac)", "hbm", st["assemble_ms"], jac * bytes_asm_jac + nres * bytes_asm_res, "GB/s", hbm_peak,
         bytes_asm_jac, jac, "forward-difference Jacobian assembled (residual requests counted at %d B each)" % bytes_asm_res)
     return kern
@@ -603,7 +764,8 @@ def main():
         ms_prof = e0.elapsed_time(e1)
         sp = eng.stats()
         eng.set_profiling(False)
-        kern = kernel_rooflines(sp, ms_prof, P, flops, peak_tf, hbm_peak, traffic)
+        import scenarios as S
+        kern = kernel_rooflines(sp, ms_prof, P, flops, peak_tf, hbm_peak, traffic, N=2 * S.DIM[w.model], M=w.M)
         dom = max(kern, key=lambda k: kern[k]["ms"])
         dk = kern[dom]
         n_launch = max(sp["solver_rounds"], 1.0)
@@ -633,7 +795,7 @@ def main():
     rk4_rate = rk4_steps_per_step * world / (ms_per_step * 1e-3)
 
     # keep the stage-1 results of the sample for the parity object before anything overwrites them
-    n_par = min(args.parity_sample, B) if pool is not None else 0
+    n_par = min(args.parity_sample, B, PARITY_CAP.get(w.name, 1 << 30)) if pool is not None else 0
     g1 = (d["info"][:n_par].cpu().numpy(), d["nfev"][:n_par].cpu().numpy(), d["x"][:n_par].cpu().numpy()) if n_par else None
 
     # ---- the RK4 trajectory kernel alone (BASELINE metric "RK4 steps/sec, % of FP64 roofline") ---------------
@@ -668,16 +830,24 @@ def main():
     # ---- CPU baseline + parity on the same sample (rank 0, N = 1) --------------------------------------------
     cpu_baseline, parity, stage2 = None, None, None
     if pool is not None:
-        n_s = args.cpu_sample or n_par
-        specs = [w.spec(k) for k in range(max(n_s, n_par))]
-        dt, res = pool.solve(specs[:max(n_s, n_par)])
+        n_s = max(args.cpu_sample or n_par, n_par)
+        specs = [w.spec(k) for k in range(n_s)]
+        dt, res = pool.work(specs)
         nf = sum(r[1] for r in res)
-        cpu_baseline = {"value": len(res) / dt, "unit": "solves/s", "cores": pool.cores, "kind": pool.kind,
+        cpu_baseline = {"value": len(res) / dt, "unit": w.unit, "cores": pool.cores,
+                        "kind": "port" if w.ode_tol > 0 else pool.kind,
                         "sample": "first %d problems of the same batch, one process per core, wall time" % len(res),
-                        "rk4_steps_per_s": nf * w.M * w.steps / dt,
+                        "rk4_steps_per_s": (nf * w.M * w.steps / dt) if w.ode_tol == 0 else None,
                         "converged_fraction": sum(1 for r in res if r[0] == 1) / len(res)}
+        if w.ode_tol > 0:
+            cpu_baseline["note"] = ("adaptive Dormand-Prince is the reference's -D_USE_BOOST build; Boost.Odeint is absent, so the "
+                                    "checker is the C port of the same algorithm (parity unpinned against Boost itself)")
         parity = parity_solve(g1[0], g1[1], g1[2], res[:n_par], w.xtol)
         parity["workload"] = w.name
+        if w.kind != "solve":
+            gc = d["calls"][:n_par, 0].cpu().numpy()
+            parity["identical_solver_calls"] = float(np.mean(gc == np.array([r[3] for r in res[:n_par]])))
+            parity["nfev_is"] = "total over the solver calls of a homotopy"
         if w.name == "goddard":
             n_e = min(128, n_par)
             _, ens = pool.run("ensemble", specs[:n_e], dict(runs=5))
@@ -695,7 +865,8 @@ def main():
     if rank == 0:
         conv = float(agg[1].item()) / total_B
         line = {
-            "metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": world, "steps": args.steps,
+            "metric": METRIC if w.name.startswith("goddard") else "shooting %s (%s)" % (w.unit.replace("/s", "/sec"), w.label),
+            "value": value, "unit": w.unit, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": w.label,
@@ -705,8 +876,9 @@ def main():
             "rk4_steps_per_s": rk4_rate, "rk4_steps_per_step": rk4_steps_per_step * world,
             "converged_fraction": conv,                                            # info == 1, what SOCP accepts
             "converged_solves_per_s": value * conv,
-            "true_root_fraction": float(agg[3].item()) / total_B,                  # info == 1 and |F| < 1e-5
+            "true_root_fraction": (float(agg[3].item()) / total_B) if w.kind == "solve" else None,   # info == 1 and |F| < 1e-5
             "mean_nfev": float(agg[2].item()) / total_B,
+            "mean_solver_calls": float(d["calls"][:, 0].double().mean().item()) if w.kind != "solve" else 1.0,
             "solver_rounds_per_step": st["solver_rounds"] / (args.steps + args.warmup),
             "gpu_launches": int(st["kernel_launches"] * args.steps / (args.steps + args.warmup)),
             "roofline": roofline, "whole_solve": whole, "rk4_kernel": rk4_kernel, "e2e": e2e, "cpu_baseline": cpu_baseline,

@@ -3,7 +3,7 @@
 // xtol 1e-6, KD = 0, mu2 = 1) solved in one batch, then the reference's first continuation (KD -> 310,
 // tests/testGoddard.cpp:105) on the whole batch.  Problem 0 is the unperturbed reference problem and is
 // also solved alone through `shooting` to show that batch membership does not change a result.
-//   usage: demo_goddard_batch [B=256]
+//   usage: demo_goddard_batch [B=256] [numDevice=1]      (numDevice 0: every visible GPU shares the batch)
 #include <cstdio>
 #include <cstdlib>
 #include <iostream>
@@ -20,6 +20,7 @@ static double unit(unsigned long long & s) {		// uniform in [-1, 1]
 
 int main(int argc, char **argv) {
 	const long B = argc > 1 ? atol(argv[1]) : 256;
+	const int numDevice = argc > 2 ? atoi(argv[2]) : 1;
 	const int M = 6;
 	goddard my_goddard("", 10);
 	const int dim = my_goddard.GetDim();
@@ -34,7 +35,8 @@ int main(int argc, char **argv) {
 
 	// the guess for the interior nodes is integrated with the constructor's KD = 310; the solve uses KD = 0
 	my_goddard.SetParameterDataName("mu2", 1.0);
-	shooting_batch batch(my_goddard, M, B);
+	shooting_batch batch(my_goddard, M, B, numDevice);
+	printf("batch of %ld problems on %d GPU(s)\n", B, batch.GetNumDevice());
 	batch.SetPrecision(1e-6);
 	batch.SetMode(model::FREE, mode_Xf);
 	std::vector<real> vti(B, ti), vtf(B, tf);

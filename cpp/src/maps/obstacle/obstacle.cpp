@@ -114,11 +114,7 @@ void obstacle::Upload() const {
 	if (data->uploaded) return;
 	std::vector<real> type, pos, rad;
 	Table(type, pos, rad);
-	socp_ctx *ctx = model::Context();
-	if (socp_set_obstacles(ctx, Count(), type.data(), pos.data(), rad.data()) != SOCP_OK) {
-		std::cerr << std::endl << "socp_b200: " << socp_last_error(ctx) << std::endl;
-		exit(1);
-	}
+	model::SetDeviceObstacles(Count(), type.data(), pos.data(), rad.data());     // every engine context, present and future
 	data->uploaded = true;
 }
 

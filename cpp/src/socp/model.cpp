@@ -5,25 +5,76 @@
 #include <cstdlib>
 #include <iostream>
 #include <sstream>
+#include <map>
+#include <mutex>
+#include <vector>
 
 #include "model.hpp"
 #include "../../../include/socp_b200.h"
 
 namespace {
-socp_ctx *g_ctx = nullptr;
+// one engine context per CUDA device, created on first use
+std::mutex g_mutex;
+std::map<int, socp_ctx *> g_ctx;
+struct ObstacleTable { int n; std::vector<real> type, pos, rad; bool set; ObstacleTable() : n(0), set(false) {} } g_obs;
 
 void die(const char *what, socp_ctx *ctx) {
 	std::cerr << std::endl << "socp_b200: " << what << ": " << socp_last_error(ctx) << std::endl;
 	exit(1);
 }
+
+int default_device() {
+	const char *dev = getenv("SOCP_DEVICE");
+	return dev ? atoi(dev) : 0;
+}
 }
 
-socp_ctx *model::Context() {
-	if (!g_ctx) {
-		const char *dev = getenv("SOCP_DEVICE");
-		if (socp_create(dev ? atoi(dev) : 0, &g_ctx) != SOCP_OK) die("socp_create", nullptr);
+socp_ctx *model::Context() { return Context(default_device()); }
+
+socp_ctx *model::Context(int device) {
+	std::lock_guard<std::mutex> lock(g_mutex);
+	std::map<int, socp_ctx *>::iterator it = g_ctx.find(device);
+	if (it != g_ctx.end()) return it->second;
+	socp_ctx *ctx = nullptr;
+	if (socp_create(device, &ctx) != SOCP_OK) die("socp_create", nullptr);
+	if (g_obs.set && socp_set_obstacles(ctx, g_obs.n, g_obs.type.data(), g_obs.pos.data(), g_obs.rad.data()) != SOCP_OK)
+		die("socp_set_obstacles", ctx);
+	g_ctx[device] = ctx;
+	return ctx;
+}
+
+int model::DeviceCount() {
+	// the engine is the only CUDA user of this library: ask it by creating contexts until one fails would be
+	// wasteful, so the count comes from the environment the runtime itself honours, else from a probe
+	int n = 0;
+	socp_ctx *probe = nullptr;
+	while (n < 64) {
+		{
+			std::lock_guard<std::mutex> lock(g_mutex);
+			if (g_ctx.count(n)) { ++n; continue; }
+		}
+		if (socp_create(n, &probe) != SOCP_OK) break;
+		{
+			std::lock_guard<std::mutex> lock(g_mutex);
+			if (g_obs.set) socp_set_obstacles(probe, g_obs.n, g_obs.type.data(), g_obs.pos.data(), g_obs.rad.data());
+			g_ctx[n] = probe;
+		}
+		++n;
 	}
-	return g_ctx;
+	return n;
+}
+
+void model::SetDeviceObstacles(int n, const real *type, const real *pos, const real *rad) {
+	std::lock_guard<std::mutex> lock(g_mutex);
+	g_obs.n = n; g_obs.set = true;
+	g_obs.type.assign(type, type + n); g_obs.pos.assign(pos, pos + 3 * n); g_obs.rad.assign(rad, rad + 3 * n);
+	if (g_ctx.empty()) {
+		socp_ctx *ctx = nullptr;
+		if (socp_create(default_device(), &ctx) != SOCP_OK) die("socp_create", nullptr);
+		g_ctx[default_device()] = ctx;
+	}
+	for (std::map<int, socp_ctx *>::iterator it = g_ctx.begin(); it != g_ctx.end(); ++it)
+		if (socp_set_obstacles(it->second, n, type, pos, rad) != SOCP_OK) die("socp_set_obstacles", it->second);
 }
 
 model::model(int const& _stateDim, int _modelOrder, int _stepNbr, std::string _fileTrace)

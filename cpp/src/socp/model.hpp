@@ -78,7 +78,13 @@ public:
 	/// end of a trace row: H, then whatever the model appends (goddard: switching function,
 	/// goddard.cpp:337; interceptor: chart id, interceptor.cpp:151); `extra` is the device's last column
 	virtual void TraceTail(real H, real extra, std::ostream & file) const;
-	static socp_ctx* Context();					///< process-wide engine context (device 0 or $SOCP_DEVICE)
+	static socp_ctx* Context();					///< engine context of the default device (device 0 or $SOCP_DEVICE)
+	/// engine context of CUDA device `device` (one context per device, created on first use; thread safe).
+	/// The obstacle table set through SetDeviceObstacles is replayed on every context created later.
+	static socp_ctx* Context(int device);
+	static int DeviceCount();					///< CUDA devices visible to this process
+	/// vtolUAV penalty map on every engine context of the process (existing and future ones)
+	static void SetDeviceObstacles(int n, const real *type, const real *pos, const real *rad);
 
 private:
 	model() {};

@@ -2,7 +2,9 @@
 // work is socp_traj_batch / socp_solve_batch / socp_continuation_*_batch (include/socp_b200.h).
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <iostream>
+#include <thread>
 
 #include "shooting_batch.hpp"
 #include "../../../include/socp_b200.h"
@@ -20,6 +22,24 @@ struct shooting_batch::data_struct {
 	std::vector<int> info, nfev, calls;
 	std::vector<real> fnorm;
 	int np;
+	int numDevice;
+	std::vector<int> devices;				// CUDA device of every block
+
+	// run f(ctx, lo, hi) for the contiguous block [lo, hi) of every device, one host thread per device
+	// (a context is used by one thread at a time: the blocks are disjoint and each thread has its own context)
+	void for_each_block(std::function<void(socp_ctx *, long, long)> f) const {
+		const int G = numDevice;
+		const long per = (B + G - 1) / G;
+		if (G == 1) { f(model::Context(devices[0]), 0, B); return; }
+		std::vector<std::thread> pool;
+		for (int g = 0; g < G; g++) {
+			const long lo = std::min<long>(g * per, B), hi = std::min<long>(lo + per, B);
+			if (hi <= lo) continue;
+			socp_ctx *ctx = model::Context(devices[g]);		// created here, in the calling thread, in device order
+			pool.push_back(std::thread(f, ctx, lo, hi));
+		}
+		for (size_t t = 0; t < pool.size(); t++) pool[t].join();
+	}
 };
 
 static void fail(socp_ctx *ctx, const char *what) {
@@ -27,7 +47,7 @@ static void fail(socp_ctx *ctx, const char *what) {
 	exit(1);
 }
 
-shooting_batch::shooting_batch(model & model, int numMulti, long batch) : myModel(model) {
+shooting_batch::shooting_batch(model & model, int numMulti, long batch, int numDevice) : myModel(model) {
 	if (numMulti < 1 || numMulti >= SOCP_MAX_NODES || batch < 1 || model.DeviceModelId() < 0) {
 		std::cerr << std::endl << "ERROR : shooting_batch needs 1 <= numMulti < " << SOCP_MAX_NODES
 		          << ", batch >= 1 and a model with a device implementation" << std::endl;
@@ -35,6 +55,13 @@ shooting_batch::shooting_batch(model & model, int numMulti, long batch) : myMode
 	}
 	data = new data_struct;
 	data->B = batch;
+	{
+		const int visible = (numDevice == 1) ? 1 : model::DeviceCount();
+		data->numDevice = (numDevice <= 0) ? visible : std::min(numDevice, visible);
+		if (data->numDevice < 1) data->numDevice = 1;
+		const char *dev = getenv("SOCP_DEVICE");
+		for (int g = 0; g < data->numDevice; g++) data->devices.push_back(data->numDevice == 1 && dev ? atoi(dev) : g);
+	}
 	data->dim = model.GetDim();
 	data->numMulti = numMulti;
 	data->xtol = 1e-8;						// shooting.cpp:95-101
@@ -62,6 +89,7 @@ shooting_batch::shooting_batch(model & model, int numMulti, long batch) : myMode
 shooting_batch::~shooting_batch() { delete data; }
 
 long shooting_batch::GetBatch() const { return data->B; }
+int shooting_batch::GetNumDevice() const { return data->numDevice; }
 int shooting_batch::GetNumParam() const { return data->numParam; }
 
 void shooting_batch::SetMode(int const& mode_tf, std::vector<int> const& mode_Xf) {
@@ -94,7 +122,6 @@ std::vector<real> shooting_batch::GetModelParameters(long k) const {
 
 void shooting_batch::InitShooting(std::vector<real> const& ti, std::vector<model::mstate> const& Xi,
                                   std::vector<real> const& tf, std::vector<model::mstate> const& Xf) {
-	socp_ctx *ctx = model::Context();
 	const long B = data->B;
 	const int M = data->numMulti, n = data->dim, N = 2 * n, P = data->numParam, nodes = M + 1;
 	std::vector<real> X0((size_t)B * N), tnode(B), Xnode((size_t)B * N);
@@ -112,9 +139,13 @@ void shooting_batch::InitShooting(std::vector<real> const& ti, std::vector<model
 	}
 	for (int i = 1; i < M; i++) {				// interior nodes: the guess integrated from ti (shooting.cpp:218-222)
 		for (long k = 0; k < B; k++) tnode[k] = data->time[k * nodes + i];
-		if (socp_traj_batch(ctx, data->shape.model_id, data->shape.step_nbr, B, data->mparams.data(), nullptr, ti.data(),
-		                    tnode.data(), X0.data(), Xnode.data(), SOCP_HOST) != SOCP_OK)
-			fail(ctx, "socp_traj_batch");
+		data_struct *d = data;
+		const int np = data->np;
+		data->for_each_block([&, d, np, N](socp_ctx *ctx, long lo, long hi) {
+			if (socp_traj_batch(ctx, d->shape.model_id, d->shape.step_nbr, hi - lo, d->mparams.data() + lo * np, nullptr,
+			                    ti.data() + lo, tnode.data() + lo, X0.data() + lo * N, Xnode.data() + lo * N, SOCP_HOST) != SOCP_OK)
+				fail(ctx, "socp_traj_batch");
+		});
 		for (long k = 0; k < B; k++) {
 			for (int j = 0; j < N; j++) data->param[k * P + N * i + j] = Xnode[k * N + j];
 			for (int j = 0; j < n; j++) data->X[(k * nodes + i) * n + j] = Xnode[k * N + j];
@@ -171,17 +202,21 @@ static long count_ok(std::vector<int> const& info) {
 }
 
 long shooting_batch::SolveOCP(real const& continuationStep) {
-	socp_ctx *ctx = model::Context();
 	const long B = data->B;
-	const int P = data->numParam;
+	const int P = data->numParam, np = data->np;
+	const size_t nodes = data->numMulti + 1, n = data->dim;
+	data_struct *d = data;
 	if (continuationStep <= 0) {
 		// SolveShooting (shooting.cpp:568-595): current data <- desired data, accept iff info == 1
 		data->time = data->timed;
 		data->X = data->Xd;
 		std::vector<real> trial(data->param);
-		if (socp_solve_batch(ctx, &data->shape, B, data->mparams.data(), data->time.data(), data->X.data(), trial.data(),
-		                     data->xtol, data->maxfev, data->info.data(), data->nfev.data(), data->fnorm.data(), SOCP_HOST) != SOCP_OK)
-			fail(ctx, "socp_solve_batch");
+		data->for_each_block([&, d](socp_ctx *ctx, long lo, long hi) {
+			if (socp_solve_batch(ctx, &d->shape, hi - lo, d->mparams.data() + lo * np, d->time.data() + lo * nodes,
+			                     d->X.data() + lo * nodes * n, trial.data() + lo * P, d->xtol, d->maxfev, d->info.data() + lo,
+			                     d->nfev.data() + lo, d->fnorm.data() + lo, SOCP_HOST) != SOCP_OK)
+				fail(ctx, "socp_solve_batch");
+		});
 		for (long k = 0; k < B; k++) {
 			data->calls[k] = 1;
 			if (data->info[k] == 1) std::copy(trial.begin() + k * P, trial.begin() + (k + 1) * P, data->param.begin() + k * P);
@@ -189,11 +224,14 @@ long shooting_batch::SolveOCP(real const& continuationStep) {
 		return count_ok(data->info);
 	}
 	std::vector<int> calls(2 * B);
-	if (socp_continuation_boundary_batch(ctx, &data->shape, B, data->mparams.data(), data->time_prec.data(), data->X_prec.data(),
-	                                     data->timed.data(), data->Xd.data(), data->param.data(), data->xtol, data->maxfev,
-	                                     continuationStep, data->stepMin, data->info.data(), calls.data(), SOCP_HOST) != SOCP_OK)
-		fail(ctx, "socp_continuation_boundary_batch");
-	const size_t nodes = data->numMulti + 1, n = data->dim;
+	data->for_each_block([&, d](socp_ctx *ctx, long lo, long hi) {
+		if (socp_continuation_boundary_batch(ctx, &d->shape, hi - lo, d->mparams.data() + lo * np, d->time_prec.data() + lo * nodes,
+		                                     d->X_prec.data() + lo * nodes * n, d->timed.data() + lo * nodes,
+		                                     d->Xd.data() + lo * nodes * n, d->param.data() + lo * P, d->xtol, d->maxfev,
+		                                     continuationStep, d->stepMin, d->info.data() + lo, calls.data() + 2 * lo,
+		                                     SOCP_HOST) != SOCP_OK)
+			fail(ctx, "socp_continuation_boundary_batch");
+	});
 	for (long k = 0; k < B; k++) {
 		data->calls[k] = calls[2 * k];
 		data->nfev[k] = calls[2 * k + 1];
@@ -206,15 +244,20 @@ long shooting_batch::SolveOCP(real const& continuationStep) {
 }
 
 long shooting_batch::SolveOCP(real const& continuationStep, int paramIndex, std::vector<real> const& goal) {
-	socp_ctx *ctx = model::Context();
 	const long B = data->B;
+	const int P = data->numParam, np = data->np;
+	const size_t nodes = data->numMulti + 1, n = data->dim;
+	data_struct *d = data;
 	data->time = data->timed;
 	data->X = data->Xd;
 	std::vector<int> calls(2 * B);
-	if (socp_continuation_param_batch(ctx, &data->shape, B, data->mparams.data(), data->time.data(), data->X.data(),
-	                                  data->param.data(), data->xtol, data->maxfev, continuationStep <= 0 ? 1.0 : continuationStep,
-	                                  paramIndex, goal.data(), data->stepMin, data->info.data(), calls.data(), SOCP_HOST) != SOCP_OK)
-		fail(ctx, "socp_continuation_param_batch");
+	data->for_each_block([&, d](socp_ctx *ctx, long lo, long hi) {
+		if (socp_continuation_param_batch(ctx, &d->shape, hi - lo, d->mparams.data() + lo * np, d->time.data() + lo * nodes,
+		                                  d->X.data() + lo * nodes * n, d->param.data() + lo * P, d->xtol, d->maxfev,
+		                                  continuationStep <= 0 ? 1.0 : continuationStep, paramIndex, goal.data() + lo, d->stepMin,
+		                                  d->info.data() + lo, calls.data() + 2 * lo, SOCP_HOST) != SOCP_OK)
+			fail(ctx, "socp_continuation_param_batch");
+	});
 	for (long k = 0; k < B; k++) { data->calls[k] = calls[2 * k]; data->nfev[k] = calls[2 * k + 1]; }
 	return count_ok(data->info);
 }

@@ -13,10 +13,14 @@
 class shooting_batch
 {
 public:
-	shooting_batch(model & model, int numMulti, long batch);
+	/// numDevice GPUs share the batch (contiguous blocks, one host thread + one engine context per device,
+	/// no communication during the solve) -- the batch analogue of the reference's `numThread` constructor
+	/// argument (shooting.hpp ctor, shooting.cpp:1133).  numDevice <= 0: every visible device.
+	shooting_batch(model & model, int numMulti, long batch, int numDevice = 1);
 	~shooting_batch();
 
 	long GetBatch() const;
+	int GetNumDevice() const;
 	int GetNumParam() const;
 
 	void SetMode(int const& mode_tf, std::vector<int> const& mode_Xf);

@@ -4,7 +4,8 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(HERE, "libsocp_b200.so")
+# SOCP_LIB selects another build of the same library (the -fmad=false parity build, socp_b200/build.py)
+SO_PATH = os.environ.get("SOCP_LIB") or os.path.join(HERE, "libsocp_b200.so")
 
 MAX_NODES, MAX_DIM = 64, 7
 HOST, DEVICE = 0, 1

@@ -287,18 +287,21 @@ SOCP_DEV void obstacle_eval(double muObs, double phiObs, const double *pos, doub
             // "d / |d| / muObs" in each gradient component) become multiplications by 1/muObs and a sign;
             // d == 0 keeps the reference's 0/0 = NaN (which zeroes the whole component below)
             double dx = pos[0] - x, dy = pos[1] - y, dz = pos[2] - z;
-            double tx = tanh((fabs(dx) - radx) * imu);
-            double ty = tanh((fabs(dy) - rady) * imu);
-            double tz = tanh((fabs(dz) - radz) * imu);
-            double ax = 1 - tx, ay = 1 - ty, az = 1 - tz;
+            // 1 - tanh(a) = 2 r and 1 - tanh(a)^2 = 4 r (1 - r) with r = 1 / (1 + exp(2a)): one exp and one
+            // reciprocal per axis instead of a library tanh (exp + divide + range logic, ~2x the instructions)
+            // and no cancellation in 1 - tanh far inside an obstacle's shadow; exp overflow gives r = 0, the limit
+            double rx = 1.0 / (1.0 + exp(2.0 * ((fabs(dx) - radx) * imu)));
+            double ry = 1.0 / (1.0 + exp(2.0 * ((fabs(dy) - rady) * imu)));
+            double rz = 1.0 / (1.0 + exp(2.0 * ((fabs(dz) - radz) * imu)));
+            double ax = 2.0 * rx, ay = 2.0 * ry, az = 2.0 * rz;
             f = f + ax * ay * az / 8;
             if (grad) {
                 const double nan_ = __longlong_as_double(0x7ff8000000000000LL);
                 double sx = (dx == 0.) ? nan_ : copysign(imu, dx), sy = (dy == 0.) ? nan_ : copysign(imu, dy),
                        sz = (dz == 0.) ? nan_ : copysign(imu, dz);
-                g0 = g0 - sx * (1 - tx * tx) * ay * az / 8;
-                g1 = g1 - sy * (1 - ty * ty) * ax * az / 8;
-                g2 = g2 - sz * (1 - tz * tz) * ax * ay / 8;
+                g0 = g0 - sx * (4.0 * rx * (1.0 - rx)) * ay * az / 8;
+                g1 = g1 - sy * (4.0 * ry * (1.0 - ry)) * ax * az / 8;
+                g2 = g2 - sz * (4.0 * rz * (1.0 - rz)) * ax * ay / 8;
             }
         }
     }

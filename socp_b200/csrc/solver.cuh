@@ -40,6 +40,7 @@ enum { D_DELTA = 0, D_XNORM, D_FNORM, D_PNORM, D_COUNT = 4 };
 struct SolverDev {
     // shape
     int model_id, dim, N, M, S, P, nfree, np, nJ, REC, LR;
+    int LRS;                               // doubles between the packed factors of two problems: LR rounded up to even (bulk copies)
     int QS;                                // doubles between the Q / fjac matrices of two problems: P*P rounded up to an
                                            // even count, so that every matrix starts 16-byte aligned (bulk copies)
     int mode_t[SOCP_MAX_NODES];
@@ -1303,6 +1304,32 @@ __device__ void r1updt_g(int n, double *s, const double *u, double *v, double *w
     gsync<G>();
     SOCP_SUB(2);
     // apply to the columns: column i is touched by rotations j = min(i, n-2) .. 0
+    if (G == 32 && n <= 96) {
+        // one warp, three columns per lane (i = lane, lane + 32, lane + 64): the three dependent chains (one per
+        // column, through its w) advance together row by row instead of one after the other; per column the
+        // operations and their order are those of the loop below
+        const int i0 = lane, i1 = lane + 32, i2 = lane + 64;
+        const double slast = s[rowstart(n, n - 1)];
+        double w0 = (i0 == n - 1) ? slast : 0., w1 = (i1 == n - 1) ? slast : 0., w2 = (i2 == n - 1) ? slast : 0.;
+        int rs = rowstart(n, n - 2);                               // packed index of S(j, j)
+        for (int j = n - 2; j >= 0; --j) {
+            const double c = cs[j], sg = sn[j];
+            if (!(c > 1.5)) {                                      // uniform: c == 2 marks "no rotation"
+                const bool a0 = i0 >= j && i0 < n, a1 = i1 >= j && i1 < n, a2 = i2 >= j && i2 < n;
+                const double x0 = a0 ? s[rs + i0 - j] : 0., x1 = a1 ? s[rs + i1 - j] : 0., x2 = a2 ? s[rs + i2 - j] : 0.;
+                const double n0 = c * x0 - sg * w0, n1 = c * x1 - sg * w1, n2 = c * x2 - sg * w2;
+                const double v0 = sg * x0 + c * w0, v1 = sg * x1 + c * w1, v2 = sg * x2 + c * w2;
+                if (a0) { s[rs + i0 - j] = n0; w0 = v0; }
+                if (a1) { s[rs + i1 - j] = n1; w1 = v1; }
+                if (a2) { s[rs + i2 - j] = n2; w2 = v2; }
+            }
+            rs -= n - j + 1;                                       // rowstart(j - 1) = rowstart(j) - (n - (j - 1))
+        }
+        const double vl = v[n - 1];
+        if (i0 < n) w[i0] = w0 + vl * u[i0];
+        if (i1 < n) w[i1] = w1 + vl * u[i1];
+        if (i2 < n) w[i2] = w2 + vl * u[i2];
+    } else
     for (int i = tid; i < n; i += G) {
         double wi = (i == n - 1) ? s[rowstart(n, n - 1)] : 0.;
         const int jtop = (i < n - 1 ? i : n - 2);
@@ -1623,6 +1650,8 @@ SOCP_DEV void res_loop(const SolverDev &D, int cur, int per_group_doubles) {
     int *next_jac = D.lists + (size_t)((1 - cur) * 2 + 1) * D.B;
     int *next_cnt = D.counts + (1 - cur) * 2;
     const double p1 = .1, p5 = .5, p001 = .001, p0001 = 1e-4;
+    bool lean_bar_ready = false;
+    unsigned lean_parity = 0;
 
     for (long g = (long)blockIdx.x * GROUPS + grp; g < nres; g += (long)gridDim.x * GROUPS) {
         const long b = res_list[g];
@@ -1650,17 +1679,43 @@ SOCP_DEV void res_loop(const SolverDev &D, int cur, int per_group_doubles) {
         // ---- trial point evaluated: wa4 = F(x + p) ----
         long long phase_t0 = clock64();
         Work W;
-        W.x = vec; W.xe = vec + n; W.fvec = vec + 2 * n; W.diag = vec + 3 * n; W.qtf = vec + 4 * n;
-        W.wa1 = vec + 5 * n; W.wa4 = vec + 6 * n; W.wa2 = vec + 7 * n; W.wa3 = vec + 8 * n; W.scr = vec + 9 * n;
-        W.r = STAGE_R ? vec + 13 * n : D.r + (size_t)b * D.LR;
+        // LEAN (the chain kernel with R staged): only what the dependent chains touch lives in shared memory --
+        // R and nine vectors; x, xe, fvec and F(x + p) are read and written element-wise and stay in global
+        // memory.  35 KB per problem instead of 38: six problems per SM instead of five.  R travels by bulk copy.
+        constexpr bool LEAN = SPLIT && STAGE_R && G == 32;
+        if (LEAN) {
+            W.x = D.x + b * n; W.xe = D.xe + b * n; W.fvec = D.fvec + b * n; W.wa4 = D.wa4 + b * n;
+            W.diag = vec; W.qtf = vec + n; W.wa1 = vec + 2 * n; W.wa2 = vec + 3 * n; W.wa3 = vec + 4 * n; W.scr = vec + 5 * n;
+            W.r = sm + ((8 + 9 * n + 1) & ~1);                 // 16-byte aligned
+        } else {
+            W.x = vec; W.xe = vec + n; W.fvec = vec + 2 * n; W.diag = vec + 3 * n; W.qtf = vec + 4 * n;
+            W.wa1 = vec + 5 * n; W.wa4 = vec + 6 * n; W.wa2 = vec + 7 * n; W.wa3 = vec + 8 * n; W.scr = vec + 9 * n;
+            W.r = STAGE_R ? vec + 13 * n : D.r + (size_t)b * D.LRS;
+        }
         W.q = D.fjac + (size_t)b * D.QS;
         W.ldq = n;
         if (!SPLIT) l2_prefetch<G>(W.q, (size_t)n * n * sizeof(double));      // Q is first touched ~20 us from now
-        gcopy_async<G>(W.x, D.x + b * n, n); gcopy_async<G>(W.xe, D.xe + b * n, n); gcopy_async<G>(W.fvec, D.fvec + b * n, n);
-        gcopy_async<G>(W.diag, D.diag + b * n, n); gcopy_async<G>(W.qtf, D.qtf + b * n, n); gcopy_async<G>(W.wa1, D.wa1 + b * n, n);
-        gcopy_async<G>(W.wa4, D.wa4 + b * n, n);
-        if (STAGE_R) gcopy_async<G>(W.r, D.r + (size_t)b * D.LR, D.LR);
-        gcopy_async_wait();
+        if (LEAN) {
+            unsigned long long *bar = (unsigned long long *)(sm + 7);
+            if (tid == 0) {
+                if (!lean_bar_ready) mbar_init(bar, 1);
+                bulk_wait_read();                              // the previous visit's copy out has read the buffer
+                mbar_expect_tx(bar, (unsigned)D.LRS * 8u);
+                bulk_g2s(W.r, D.r + (size_t)b * D.LRS, (unsigned)D.LRS * 8u, bar);
+            }
+            lean_bar_ready = true;
+            gcopy_async<G>(W.diag, D.diag + b * n, n); gcopy_async<G>(W.qtf, D.qtf + b * n, n); gcopy_async<G>(W.wa1, D.wa1 + b * n, n);
+            gcopy_async_wait();
+            __syncwarp();
+            while (!mbar_try_wait(bar, lean_parity)) {}
+            lean_parity ^= 1u;
+        } else {
+            gcopy_async<G>(W.x, D.x + b * n, n); gcopy_async<G>(W.xe, D.xe + b * n, n); gcopy_async<G>(W.fvec, D.fvec + b * n, n);
+            gcopy_async<G>(W.diag, D.diag + b * n, n); gcopy_async<G>(W.qtf, D.qtf + b * n, n); gcopy_async<G>(W.wa1, D.wa1 + b * n, n);
+            gcopy_async<G>(W.wa4, D.wa4 + b * n, n);
+            if (STAGE_R) gcopy_async<G>(W.r, D.r + (size_t)b * D.LRS, D.LRS);
+            gcopy_async_wait();
+        }
         gsync<G>();
         SOCP_PHASE(16, 0);
 
@@ -1830,12 +1885,22 @@ SOCP_DEV void res_loop(const SolverDev &D, int cur, int per_group_doubles) {
             SOCP_PHASE(16, 6);
         }
         gsync<G>();
-        gcopy<G>(D.x + b * n, W.x, n); gcopy<G>(D.xe + b * n, W.xe, n); gcopy<G>(D.fvec + b * n, W.fvec, n);
-        gcopy<G>(D.qtf + b * n, W.qtf, n); gcopy<G>(D.wa1 + b * n, W.wa1, n);
-        if (STAGE_R && store_r) gcopy<G>(D.r + (size_t)b * D.LR, W.r, D.LR);
+        if (LEAN) {
+            gcopy<G>(D.qtf + b * n, W.qtf, n); gcopy<G>(D.wa1 + b * n, W.wa1, n);
+            if (store_r) {
+                fence_async_smem();
+                __syncwarp();
+                if (tid == 0) bulk_s2g(D.r + (size_t)b * D.LRS, W.r, (unsigned)D.LRS * 8u);
+            }
+        } else {
+            gcopy<G>(D.x + b * n, W.x, n); gcopy<G>(D.xe + b * n, W.xe, n); gcopy<G>(D.fvec + b * n, W.fvec, n);
+            gcopy<G>(D.qtf + b * n, W.qtf, n); gcopy<G>(D.wa1 + b * n, W.wa1, n);
+            if (STAGE_R && store_r) gcopy<G>(D.r + (size_t)b * D.LRS, W.r, D.LR);
+        }
         gsync<G>();
         SOCP_PHASE(16, 7);
     }
+    if (SPLIT && STAGE_R && G == 32 && tid == 0) bulk_wait_all();
 }
 
 // 4 CTAs/SM: after the instruction-level pass the kernel fits 128 registers without spills and the fourth
@@ -1897,7 +1962,7 @@ hybrd_jac_kernel(SolverDev D, int cur, int per_group_doubles) {
         W.x = vec; W.xe = vec + n; W.fvec = vec + 2 * n; W.diag = vec + 3 * n; W.qtf = vec + 4 * n;
         W.wa1 = vec + 5 * n; W.wa4 = vec + 6 * n; W.wa2 = vec + 7 * n; W.wa3 = vec + 8 * n; W.scr = vec + 9 * n;
         double *after = vec + 13 * n;
-        W.r = STAGE_R ? after : D.r + (size_t)b * D.LR;
+        W.r = STAGE_R ? after : D.r + (size_t)b * D.LRS;
         if (STAGE_R) after += D.LR;
         double *gq = D.fjac + (size_t)b * D.QS;
         if (STAGE_Q) after = sm + (((after - sm) + 1) & ~(ptrdiff_t)1);      // Q starts 16-byte aligned (bulk copies)
@@ -1961,7 +2026,7 @@ hybrd_jac_kernel(SolverDev D, int cur, int per_group_doubles) {
         gsync<G>();
         gcopy<G>(D.xe + b * n, W.xe, n); gcopy<G>(D.diag + b * n, W.diag, n);
         gcopy<G>(D.qtf + b * n, W.qtf, n); gcopy<G>(D.wa1 + b * n, W.wa1, n);
-        if (STAGE_R) gcopy<G>(D.r + (size_t)b * D.LR, W.r, D.LR);
+        if (STAGE_R) gcopy<G>(D.r + (size_t)b * D.LRS, W.r, D.LR);
         SOCP_PHASE(32, 5);
         if (bulk) {
             // the accumulated Q leaves with one bulk copy; the next problem's copy in waits for it to have read the buffer

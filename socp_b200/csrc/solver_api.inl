@@ -38,6 +38,7 @@ int make_plan(socp_ctx *ctx, const socp_shape *shape, HostPlan &pl) {
     D.np = kNP[D.model_id];
     D.REC = D.N + 2;
     D.LR = P * (P + 1) / 2;
+    D.LRS = (D.LR + 1) & ~1;
     D.QS = (P * P + 1) & ~1;
     D.nfree = P - D.N * D.M;
     D.ode_tol = (shape->integrator == SOCP_DOPRI5) ? shape->ode_tol : 0.;
@@ -68,7 +69,7 @@ int make_plan(socp_ctx *ctx, const socp_shape *shape, HostPlan &pl) {
     D.nJ = (int)pl.jac_col.size();
     pl.table_ints = 2 * (size_t)D.nJ + 2 * (size_t)P;
     // persistent bytes per problem
-    size_t dbl = (size_t)P * 10 + 4 * (size_t)P + (size_t)D.QS + D.LR + (size_t)(2 * D.M + D.nJ) * D.REC + D_COUNT;
+    size_t dbl = (size_t)P * 10 + 4 * (size_t)P + (size_t)D.QS + D.LRS + (size_t)(2 * D.M + D.nJ) * D.REC + D_COUNT;
     pl.bytes_per_problem = dbl * sizeof(double) + (I_COUNT + 4) * sizeof(int) + 2048 / 64;
     return SOCP_OK;
 }
@@ -88,7 +89,7 @@ size_t carve(HostPlan &pl, void *blob, long Bw) {
     D.wa1 = c.take<double>(Bw * P); D.wa2 = c.take<double>(Bw * P); D.wa3 = c.take<double>(Bw * P);
     D.wa4 = c.take<double>(Bw * P); D.scr = c.take<double>(Bw * 4 * P);
     D.fjac = c.take<double>(Bw * (size_t)D.QS);
-    D.r = c.take<double>(Bw * (size_t)D.LR);
+    D.r = c.take<double>(Bw * (size_t)D.LRS);
     D.ends = c.take<double>(Bw * 2 * (size_t)D.M * D.REC);
     D.jends = c.take<double>(Bw * (size_t)D.nJ * D.REC);
     D.dstate = c.take<double>(Bw * D_COUNT);
@@ -179,11 +180,12 @@ SmemPlan smem_plan(const SolverDev &D) {
     // + the mbarrier in one CTA; the chain kernel needs R + 13 vectors per warp.  SOCP_BROYDEN=fused keeps the
     // one-kernel form (A/B measurements, and the fallback when Q does not fit: P > ~165).
     p.bytes_qpass = ((size_t)D.QS + ((D.P + 1) & ~1) + 4 * (size_t)D.P + 2) * 8;
-    p.chain_doubles = (int)dr;
+    // chain kernel, lean layout: [8][9 P vectors][pad to 16 B][R, LRS doubles]
+    p.chain_doubles = (int)(((8 + 9 * (size_t)D.P + 1) & ~(size_t)1) + D.LRS);
     const char *mode = getenv("SOCP_BROYDEN");
     p.split = p.G == 128 && p.stage_r && p.bytes_qpass <= limit && !(mode && !strcmp(mode, "fused"));
     p.qpass_per_sm = (int)std::max<size_t>(1, sm_bytes / (p.bytes_qpass + 1024));
-    p.chain_per_sm = (int)std::min<size_t>(16, std::max<size_t>(1, sm_bytes / (dr * 8 + 1024)));
+    p.chain_per_sm = (int)std::min<size_t>(16, std::max<size_t>(1, sm_bytes / ((size_t)p.chain_doubles * 8 + 1024)));
     return p;
 }
 
@@ -248,7 +250,7 @@ void launch_hybrd(socp_ctx *ctx, const SolverDev &D, int cur, int grid, int prof
             // SOCP_CHAIN_R=global: the packed factor stays in global memory (L2), 16 problems per SM instead of 5
             static const bool r_global = getenv("SOCP_CHAIN_R") && !strcmp(getenv("SOCP_CHAIN_R"), "global");
             if (r_global) {
-                const int cd = sp.chain_doubles - D.LR;
+                const int cd = 8 + 13 * D.P;
                 const int gc = full ? D.sm_count * 16 * 2 : g;
                 launch_smem(ctx, hybrd_chain_kernel<false>, gc, 32, (size_t)cd * 8, D, cur, cd);
             } else {

@@ -192,3 +192,17 @@ def test_reference_interceptor_and_vtol_demos_run(tmp_path):
     backends._obstacle_files(str(d))                      # writes d/obstacles and d/waypoints
     out = _run("ref_testVtolUAV", cwd=str(run))
     assert out.count("OK = 1") == 4, out
+
+
+@pytest.mark.gpu
+def test_goddard_batch_demo_over_every_visible_gpu():
+    """shooting_batch(model, numMulti, batch, numDevice = 0): one host thread and one engine context per GPU,
+    contiguous blocks of the batch (on a one-GPU box this is the single-device path through the same code)."""
+    out = _run("demo_goddard_batch", "256", "0")
+    assert "identical to the single solve: yes" in out, out
+    m = re.search(r"batch of 256 problems on (\d+) GPU", out)
+    assert m and int(m.group(1)) >= 1, out
+    one = _run("demo_goddard_batch", "256", "1")
+    # the same problems give the same answers whatever the number of devices
+    assert re.search(r"batch 256 solved: (\d+)", out).group(1) == re.search(r"batch 256 solved: (\d+)", one).group(1)
+    assert re.search(r"problem 0: .*", out).group(0) == re.search(r"problem 0: .*", one).group(0)

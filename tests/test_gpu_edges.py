@@ -96,3 +96,63 @@ def test_device_pointers_match_host_buffers():
     eng.sync()
     assert np.array_equal(r["x"].cpu().numpy(), host["x"])
     assert np.array_equal(r["info"].cpu().numpy(), host["info"]) and np.array_equal(r["nfev"].cpu().numpy(), host["nfev"])
+
+
+def test_two_engines_in_one_process_each_configure_their_own_kernels():
+    """Opt-in shared memory (> 48 KB) is a per-device function attribute and is tracked per context: a second
+    engine -- on the second GPU when there is one, else on the same GPU -- runs the P = 85 Powell-hybrid kernels
+    (67-96 KB of dynamic shared memory) and gets the first engine's results bit for bit."""
+    import torch
+    import socp_b200 as sb
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    e0 = sb.Engine(0)
+    e1 = sb.Engine(1 if torch.cuda.device_count() > 1 else 0)
+    w = bench.wl_goddard_warm(e0, 64, seed=20260002)
+    out = []
+    for e in (e0, e1, e0):
+        x = np.ascontiguousarray(w.x0).copy()
+        r = e.solve_batch(w.shape, w.mp, w.time, w.Xb, x, xtol=w.xtol)
+        out.append((r["x"].copy(), r["info"].copy(), r["nfev"].copy()))
+    for a in out[1:]:
+        assert np.array_equal(a[0], out[0][0]) and np.array_equal(a[1], out[0][1]) and np.array_equal(a[2], out[0][2])
+    assert np.all(out[0][1] == 1)
+
+
+def test_device_tensors_are_validated():
+    """DEVICE-mode arguments are checked before their pointer crosses the C ABI: wrong dtype, wrong GPU."""
+    import torch
+    import socp_b200 as sb
+    e = sb.Engine(0)
+    X0 = torch.zeros((4, 12), dtype=torch.float32, device="cuda:0")
+    mp = torch.ones((4, 3), dtype=torch.float64, device="cuda:0")
+    t = torch.zeros(4, dtype=torch.float64, device="cuda:0")
+    with pytest.raises(ValueError):
+        e.traj_batch(sb.DOUBLE_INTEGRATOR, mp, t, X0, t + 1.0)
+
+
+def test_device_mode_follows_torch_current_stream():
+    """A DEVICE-mode call is ordered after work queued on torch's current stream without the caller doing
+    anything: the copy that fills x on a side stream must be seen by the solve."""
+    import torch
+    import socp_b200 as sb
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    e = sb.Engine(0)
+    w = bench.wl_goddard_warm(e, 2048, seed=20260002)
+    dev = torch.device("cuda", 0)
+    d = bench.device_arrays(torch, dev, w)
+    ref = e.solve_batch(w.shape, w.mp, w.time, w.Xb, np.ascontiguousarray(w.x0).copy(), xtol=w.xtol)
+    side = torch.cuda.Stream(device=dev)
+    torch.cuda.synchronize()
+    with torch.cuda.stream(side):
+        d["x"].zero_()
+        for _ in range(20):                       # keep the side stream busy before the copy that matters
+            d["x"].add_(1.0)
+        d["x"].copy_(d["x0"])
+        e.solve_batch(w.shape, d["mp"], d["time"], d["Xb"], d["x"], xtol=w.xtol, info=d["info"], nfev=d["nfev"], fnorm=d["fnorm"])
+    torch.cuda.synchronize()
+    assert np.array_equal(d["info"].cpu().numpy(), ref["info"]) and np.array_equal(d["nfev"].cpu().numpy(), ref["nfev"])
+    assert np.array_equal(d["x"].cpu().numpy(), ref["x"])
