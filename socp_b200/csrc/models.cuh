@@ -260,50 +260,82 @@ template <> struct Model<COVID19> {
 // =============================== vtolUAV + obstacle map =======================================
 // obstacle.cpp:155-178 (Function / Gradient; the waypoint terms are commented out there),
 // :183-231 (penalty) and :236-316 (gradient; the ellipsoid gradient ignores z, :260-265).
-SOCP_DEV void obstacle_eval(double muObs, double phiObs, const double *pos, double *func, double *grad) {
-    double f = 0, g0 = 0, g1 = 0, g2 = 0;
+// The sum over the obstacles has ONE canonical order whatever the thread mapping: four partial sums over the
+// obstacles i = q (mod 4), combined as (s0 + s2) + (s1 + s3).  One thread per trajectory keeps the four partial
+// sums itself; a cooperative group of four lanes per trajectory (coop_lanes == 4: lane q owns the obstacles
+// i = q (mod 4), two xor-shuffles combine) produces the same bits, so a trajectory does not depend on which of the
+// two kernels integrated it.
+struct ObsAcc { double f, g0, g1, g2; };
+SOCP_DEV void obstacle_one(int i, double muObs, double imu, const double *pos, bool want_f, bool want_g, ObsAcc &a) {
+    const double *o = &c_obstacles[i * 7];
+    double type = o[0], x = o[1], y = o[2], z = o[3], radx = o[4], rady = o[5], radz = o[6];
+    if (type == 0) {
+        double hx = pos[0] - x, hy = pos[1] - y, hz = pos[2] - z;
+        double d = sqrt(hx * hx + hy * hy + hz * hz);
+        if (want_f) {
+            double rad = d / sqrt(hx * hx / radx / radx + hy * hy / rady / rady + hz * hz / radz / radz);
+            a.f = a.f + (1 - tanh((d - rad) / muObs)) / 2;
+        }
+        if (want_g) {
+            double sq = sqrt(hx * hx / radx / radx + hy * hy / rady / rady);
+            double rad = d / sq;
+            double th = tanh((d - rad) / muObs);
+            double rho2 = (radx * radx - rady * rady) / (radx * radx * rady * rady) / sq / sq / sq;
+            a.g0 = a.g0 - hx / d * (1 - hy * hy * rho2) / muObs * (1 - th * th) / 2;
+            a.g1 = a.g1 - hy / d * (1 + hx * hx * rho2) / muObs * (1 - th * th) / 2;
+        }
+    } else if (type == 1) {
+        // box: the nine divides per obstacle of the reference (three "/ muObs" in the tanh arguments and
+        // "d / |d| / muObs" in each gradient component) become multiplications by 1/muObs and a sign;
+        // d == 0 keeps the reference's 0/0 = NaN (which zeroes the whole component below)
+        double dx = pos[0] - x, dy = pos[1] - y, dz = pos[2] - z;
+        // 1 - tanh(a) = 2 r and 1 - tanh(a)^2 = 4 r (1 - r) with r = 1 / (1 + exp(2a)): one exp and one
+        // reciprocal per axis instead of a library tanh (exp + divide + range logic, ~2x the instructions)
+        // and no cancellation in 1 - tanh far inside an obstacle's shadow; exp overflow gives r = 0, the limit
+        double rx = 1.0 / (1.0 + exp(2.0 * ((fabs(dx) - radx) * imu)));
+        double ry = 1.0 / (1.0 + exp(2.0 * ((fabs(dy) - rady) * imu)));
+        double rz = 1.0 / (1.0 + exp(2.0 * ((fabs(dz) - radz) * imu)));
+        double ax = 2.0 * rx, ay = 2.0 * ry, az = 2.0 * rz;
+        a.f = a.f + ax * ay * az / 8;
+        if (want_g) {
+            const double nan_ = __longlong_as_double(0x7ff8000000000000LL);
+            double sx = (dx == 0.) ? nan_ : copysign(imu, dx), sy = (dy == 0.) ? nan_ : copysign(imu, dy),
+                   sz = (dz == 0.) ? nan_ : copysign(imu, dz);
+            a.g0 = a.g0 - sx * (4.0 * rx * (1.0 - rx)) * ay * az / 8;
+            a.g1 = a.g1 - sy * (4.0 * ry * (1.0 - ry)) * ax * az / 8;
+            a.g2 = a.g2 - sz * (4.0 * rz * (1.0 - rz)) * ax * ay / 8;
+        }
+    }
+}
+
+// coop_lanes == 1: this thread evaluates every obstacle; == 4: it is lane `cq` of a group of four (shuffle mask `cmask`)
+SOCP_DEV void obstacle_eval(double muObs, double phiObs, const double *pos, double *func, double *grad,
+                            int coop_lanes = 1, int cq = 0, unsigned cmask = 0) {
     const double imu = 1.0 / muObs;
     const int n = c_num_obstacles;
-    for (int i = 0; i < n; ++i) {
-        const double *o = &c_obstacles[i * 7];
-        double type = o[0], x = o[1], y = o[2], z = o[3], radx = o[4], rady = o[5], radz = o[6];
-        if (type == 0) {
-            double hx = pos[0] - x, hy = pos[1] - y, hz = pos[2] - z;
-            double d = sqrt(hx * hx + hy * hy + hz * hz);
-            if (func) {
-                double rad = d / sqrt(hx * hx / radx / radx + hy * hy / rady / rady + hz * hz / radz / radz);
-                f = f + (1 - tanh((d - rad) / muObs)) / 2;
-            }
-            if (grad) {
-                double sq = sqrt(hx * hx / radx / radx + hy * hy / rady / rady);
-                double rad = d / sq;
-                double th = tanh((d - rad) / muObs);
-                double rho2 = (radx * radx - rady * rady) / (radx * radx * rady * rady) / sq / sq / sq;
-                g0 = g0 - hx / d * (1 - hy * hy * rho2) / muObs * (1 - th * th) / 2;
-                g1 = g1 - hy / d * (1 + hx * hx * rho2) / muObs * (1 - th * th) / 2;
-            }
-        } else if (type == 1) {
-            // box: the nine divides per obstacle of the reference (three "/ muObs" in the tanh arguments and
-            // "d / |d| / muObs" in each gradient component) become multiplications by 1/muObs and a sign;
-            // d == 0 keeps the reference's 0/0 = NaN (which zeroes the whole component below)
-            double dx = pos[0] - x, dy = pos[1] - y, dz = pos[2] - z;
-            // 1 - tanh(a) = 2 r and 1 - tanh(a)^2 = 4 r (1 - r) with r = 1 / (1 + exp(2a)): one exp and one
-            // reciprocal per axis instead of a library tanh (exp + divide + range logic, ~2x the instructions)
-            // and no cancellation in 1 - tanh far inside an obstacle's shadow; exp overflow gives r = 0, the limit
-            double rx = 1.0 / (1.0 + exp(2.0 * ((fabs(dx) - radx) * imu)));
-            double ry = 1.0 / (1.0 + exp(2.0 * ((fabs(dy) - rady) * imu)));
-            double rz = 1.0 / (1.0 + exp(2.0 * ((fabs(dz) - radz) * imu)));
-            double ax = 2.0 * rx, ay = 2.0 * ry, az = 2.0 * rz;
-            f = f + ax * ay * az / 8;
-            if (grad) {
-                const double nan_ = __longlong_as_double(0x7ff8000000000000LL);
-                double sx = (dx == 0.) ? nan_ : copysign(imu, dx), sy = (dy == 0.) ? nan_ : copysign(imu, dy),
-                       sz = (dz == 0.) ? nan_ : copysign(imu, dz);
-                g0 = g0 - sx * (4.0 * rx * (1.0 - rx)) * ay * az / 8;
-                g1 = g1 - sy * (4.0 * ry * (1.0 - ry)) * ax * az / 8;
-                g2 = g2 - sz * (4.0 * rz * (1.0 - rz)) * ax * ay / 8;
-            }
+    double f, g0, g1, g2;
+    if (coop_lanes == 4) {
+        ObsAcc a = {0., 0., 0., 0.};
+        for (int i = cq; i < n; i += 4) obstacle_one(i, muObs, imu, pos, func != nullptr, grad != nullptr, a);
+        f = a.f + __shfl_xor_sync(cmask, a.f, 2); f = f + __shfl_xor_sync(cmask, f, 1);
+        g0 = a.g0 + __shfl_xor_sync(cmask, a.g0, 2); g0 = g0 + __shfl_xor_sync(cmask, g0, 1);
+        g1 = a.g1 + __shfl_xor_sync(cmask, a.g1, 2); g1 = g1 + __shfl_xor_sync(cmask, g1, 1);
+        g2 = a.g2 + __shfl_xor_sync(cmask, a.g2, 2); g2 = g2 + __shfl_xor_sync(cmask, g2, 1);
+    } else {
+        // the same four partial sums one after the other, in the order 0, 2, 1, 3 (one inlined copy of the
+        // obstacle code, twelve live doubles): (s0 + s2) + (s1 + s3)
+        ObsAcc acc = {0., 0., 0., 0.}, t02 = acc;
+#pragma unroll 1
+        for (int k = 0; k < 4; ++k) {
+            const int q = ((k & 1) << 1) | (k >> 1);
+            ObsAcc a = {0., 0., 0., 0.};
+#pragma unroll 1
+            for (int i = q; i < n; i += 4) obstacle_one(i, muObs, imu, pos, func != nullptr, grad != nullptr, a);
+            if (k == 2) { t02 = acc; acc = a; }
+            else if (k == 0) acc = a;
+            else { acc.f = acc.f + a.f; acc.g0 = acc.g0 + a.g0; acc.g1 = acc.g1 + a.g1; acc.g2 = acc.g2 + a.g2; }
         }
+        f = t02.f + acc.f; g0 = t02.g0 + acc.g0; g1 = t02.g1 + acc.g1; g2 = t02.g2 + acc.g2;
     }
     if (func) *func = phiObs * (isnan(f) ? 0.0 : f);
     if (grad) {
@@ -316,10 +348,12 @@ SOCP_DEV void obstacle_eval(double muObs, double phiObs, const double *pos, doub
 template <> struct Model<VTOL_UAV> {
     static constexpr int DIM = 6, N = 12, NP = 13, NCTRL = 3, DEFAULT_STEPS = 100;
     static constexpr int MINB = 4;      // 128 registers: +45% throughput (occupancy hides the tanh chains)
-    struct Ctx { double umax, amax, alphaT, alphaV, invSigma, Vd, ca, phiObs, muObs; };
+    // coop_lanes / cq / cmask: the thread mapping of the obstacle sum (see obstacle_eval), set by the cooperative kernels
+    struct Ctx { double umax, amax, alphaT, alphaV, invSigma, Vd, ca, phiObs, muObs; int coop_lanes, cq; unsigned cmask; };
     SOCP_DEV static void load(Ctx &c, const double *m, const double *) {
         c.umax = m[0]; c.amax = m[1]; c.alphaT = m[2]; c.alphaV = m[3]; c.invSigma = m[4];
         c.Vd = m[5]; c.ca = m[6]; c.phiObs = m[9]; c.muObs = m[11];
+        c.coop_lanes = 1; c.cq = 0; c.cmask = 0;
     }
     // vtolUAV.cpp:110-148
     SOCP_DEV static void control(const Ctx &c, double, const double *X, double *u) {
@@ -336,7 +370,7 @@ template <> struct Model<VTOL_UAV> {
         double normV = sqrt(vx * vx + vy * vy + vz * vz);
         double u[3], grad[3];
         control(c, t, X, u);
-        obstacle_eval(c.muObs, c.phiObs, X, nullptr, grad);
+        obstacle_eval(c.muObs, c.phiObs, X, nullptr, grad, c.coop_lanes, c.cq, c.cmask);
         dX[0] = vx; dX[1] = vy; dX[2] = vz;
         dX[3] = c.amax * u[0] - c.ca * vx * normV;
         dX[4] = c.amax * u[1] - c.ca * vy * normV;
@@ -355,7 +389,7 @@ template <> struct Model<VTOL_UAV> {
         double u[3], obs = 0;
         control(c, t, X, u);
         double nu = sqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
-        obstacle_eval(c.muObs, c.phiObs, X, &obs, nullptr);
+        obstacle_eval(c.muObs, c.phiObs, X, &obs, nullptr, c.coop_lanes, c.cq, c.cmask);
         return c.alphaT * 1 + c.alphaV / 2 * (normV - c.Vd) * (normV - c.Vd) + obs + c.amax * c.amax * nu * nu / 2
              + p_x * vx + p_y * vy + p_z * vz
              + (p_vx * (c.amax * u[0] - c.ca * vx * normV) + p_vy * (c.amax * u[1] - c.ca * vy * normV) + p_vz * (c.amax * u[2] - c.ca * vz * normV));

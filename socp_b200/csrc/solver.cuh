@@ -1713,7 +1713,7 @@ SOCP_DEV void res_loop(const SolverDev &D, int cur, int per_group_doubles) {
             gcopy_async<G>(W.x, D.x + b * n, n); gcopy_async<G>(W.xe, D.xe + b * n, n); gcopy_async<G>(W.fvec, D.fvec + b * n, n);
             gcopy_async<G>(W.diag, D.diag + b * n, n); gcopy_async<G>(W.qtf, D.qtf + b * n, n); gcopy_async<G>(W.wa1, D.wa1 + b * n, n);
             gcopy_async<G>(W.wa4, D.wa4 + b * n, n);
-            if (STAGE_R) gcopy_async<G>(W.r, D.r + (size_t)b * D.LRS, D.LRS);
+            if (STAGE_R) gcopy_async<G>(W.r, D.r + (size_t)b * D.LRS, D.LR);
             gcopy_async_wait();
         }
         gsync<G>();
