@@ -648,13 +648,21 @@ def kernel_rooflines(st, ms_profiled, P, flops_step, peak_tf, hbm_peak, traffic,
         k["traffic_per_unit"] = tr["dram_bytes_per_unit"] if tr else None
         kern[name] = k
 
-    add("integrate_worklist", "fp64", st["integrate_ms"], st["rk4_steps"] * flops_step, "TFLOP/s", peak_tf, flops_step,
-        st["rk4_steps"], "RK4 step")
+    if st["rk4_steps"] > 0:
+        add("integrate_worklist", "fp64", st["integrate_ms"], st["rk4_steps"] * flops_step, "TFLOP/s", peak_tf, flops_step,
+            st["rk4_steps"], "RK4 step")
+    else:
+        # adaptive Dormand-Prince: an accepted step is six new right-hand sides (the seventh is the next step's first)
+        # and ~40 N flops of stage algebra; rejected attempts are not counted (nominal, like the RK4 figure)
+        rhs = (flops_step - 12.0 * N) / 4.0
+        fl = 6.0 * rhs + 40.0 * N
+        add("integrate_worklist(dopri5)", "fp64", st["integrate_ms"], st["dopri_steps"] * fl, "TFLOP/s", peak_tf, fl,
+            st["dopri_steps"], "accepted Dormand-Prince step")
     # Broyden phase.  Split build: a streaming pass over Q (apply the pending 2(P-1) rotations, form Q^T f:
     # Q read + written once) and a chain kernel (R read + written once, work vectors).  Fused build: one kernel.
     bytes_q = 8.0 * (2 * P * P + 6 * P)
     bytes_chain = 8.0 * (2 * LR + 16 * P)
-    if st.get("qpass_ms", 0.0) > 0:
+    if st.get("qpass_ms", 0.0) > 0.02 * st["res_ms"]:           # the split build (the record between two events is never 0)
         add("hybrd_qpass_kernel", "hbm", st["qpass_ms"], it * bytes_q, "GB/s", hbm_peak, bytes_q, it, "Broyden iteration of one problem")
         add("hybrd_chain_kernel", "hbm", st["res_ms"] - st["qpass_ms"], it * bytes_chain, "GB/s", hbm_peak, bytes_chain, it,
             "Broyden iteration of one problem")

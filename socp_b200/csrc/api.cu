@@ -124,10 +124,29 @@ enum { SLOT_MPARAMS = 0, SLOT_SW, SLOT_T0, SLOT_TF, SLOT_X0, SLOT_XF, SLOT_AUX0,
        SLOT_TIME, SLOT_XB, SLOT_X, SLOT_FVEC, SLOT_FJAC, SLOT_INFO, SLOT_NFEV, SLOT_FNORM, SLOT_PEAK,
        SLOT_CONT, SLOT_CONT_A, SLOT_CONT_B, SLOT_SOLVER_BASE };
 
+// cooperative groups (Coop<MODEL>::LANES lanes per trajectory) when one thread per trajectory cannot fill the GPU:
+// fewer threads than the device holds at the kernel's occupancy.  SOCP_COOP=0 / 1 forces never / always.
+static bool use_coop(socp_ctx *ctx, long items, int lanes) {
+    if (lanes <= 1) return false;
+    static const char *env = getenv("SOCP_COOP");
+    if (env) return atoi(env) != 0;
+    return items * lanes <= (long)ctx->sm_count * 128 * 4;
+}
+
 template <int MODEL>
 static void launch_traj(socp_ctx *ctx, long B, int S, const double *mp, const double *sw, const double *t0,
                         const double *tf, const double *X0, double *Xf, double tol = 0., int *nsteps = nullptr) {
     const int threads = SOCP_TRAJ_THREADS;
+    constexpr int L = Coop<MODEL>::LANES;
+    if (use_coop(ctx, B, L)) {
+        const long blocks = (B * L + threads - 1) / threads;
+        if (tol > 0.)
+            traj_kernel<MODEL, true, L><<<(unsigned)blocks, threads, 0, ctx->stream>>>(B, S, mp, sw, t0, tf, X0, Xf, ctx->d_counters, tol, nsteps);
+        else
+            traj_kernel<MODEL, false, L><<<(unsigned)blocks, threads, 0, ctx->stream>>>(B, S, mp, sw, t0, tf, X0, Xf, ctx->d_counters, 0., nullptr);
+        ctx->launches += 1;
+        return;
+    }
     long blocks = (B + threads - 1) / threads;
     if (tol > 0.)
         traj_kernel<MODEL, true><<<(unsigned)blocks, threads, 0, ctx->stream>>>(B, S, mp, sw, t0, tf, X0, Xf, ctx->d_counters, tol, nsteps);

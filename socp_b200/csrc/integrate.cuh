@@ -10,6 +10,37 @@
 
 namespace socp {
 
+// ---- cooperative thread groups (north_star (1): "a warp-cooperative group for wider models such as vtolUAV") ------
+// Coop<MODEL>::LANES lanes of a warp own ONE trajectory: every lane carries the whole state (the RK4 / dopri5
+// algebra is replicated, it is a few dozen flops) and the expensive, separable part of the right-hand side is split
+// over the lanes and combined with shuffles -- for vtolUAV the sum over the obstacles of the penalty map (27 exp per
+// evaluation, 85 % of the RHS): lane q takes the obstacles i = q (mod 4).  The adaptive integrator's error norm is
+// reduced the same way (each lane the components i = q (mod LANES), then a shuffle max over the group).  The results
+// are bit for bit those of the one-thread-per-trajectory kernels (obstacle_eval fixes one summation order for both),
+// so which kernel integrates a trajectory is purely a scheduling decision: the group form is used when the batch is
+// too small to fill the GPU with one thread per trajectory (the tail of a batched solve, small batches).
+template <int MODEL> struct Coop {
+    static constexpr int LANES = 1;
+    SOCP_DEV static void set(typename Model<MODEL>::Ctx &, int, unsigned) {}
+    SOCP_DEV static bool owns(const typename Model<MODEL>::Ctx &, int) { return true; }
+    SOCP_DEV static double group_max(const typename Model<MODEL>::Ctx &, double v) { return v; }
+};
+template <> struct Coop<VTOL_UAV> {
+    static constexpr int LANES = 4;
+    SOCP_DEV static void set(Model<VTOL_UAV>::Ctx &c, int q, unsigned mask) { c.coop_lanes = LANES; c.cq = q; c.cmask = mask; }
+    SOCP_DEV static bool owns(const Model<VTOL_UAV>::Ctx &c, int i) { return c.coop_lanes == 1 || (i & (LANES - 1)) == c.cq; }
+    // max over the group with MINPACK-free NaN semantics: a NaN anywhere gives NaN (the step is rejected)
+    SOCP_DEV static double group_max(const Model<VTOL_UAV>::Ctx &c, double v) {
+        if (c.coop_lanes == 1) return v;
+#pragma unroll
+        for (int off = LANES / 2; off > 0; off >>= 1) {
+            const double o = __shfl_xor_sync(c.cmask, v, off);
+            v = (v != v || o != o) ? nan("") : fmax(v, o);
+        }
+        return v;
+    }
+};
+
 // One classical RK4 step with the reference's combination order
 //   X <- X + (h/6) * (F1 + (F4 + 2*(F2 + F3)))          (odeTools.cpp:97)
 template <int MODEL>
@@ -87,13 +118,17 @@ SOCP_DEV void dopri5_try(const typename Model<MODEL>::Ctx &c, double t, const do
     for (int i = 0; i < N; ++i)
         out[i] = in[i] + dt * c1 * k1[i] + dt * c3 * k3[i] + dt * c4 * k4[i] + dt * c5 * k5[i] + dt * c6 * k6[i];
     M::rhs(c, t + dt, out, k7);
+    // error norm (Boost's default_error_checker: max_i |xerr_i| / (eps_abs + eps_rel (|x_i| + dt |dxdt_i|))): every lane
+    // of a cooperative group takes its share of the components, a shuffle max over the group drives the step control
     err = 0.;
 #pragma unroll
     for (int i = 0; i < N; ++i) {
+        if (!Coop<MODEL>::owns(c, i)) continue;
         const double xe = dt * dc1 * k1[i] + dt * dc3 * k3[i] + dt * dc4 * k4[i] + dt * dc5 * k5[i] + dt * dc6 * k6[i] + dt * dc7 * k7[i];
         const double e = fabs(xe) / (tol + tol * (fabs(in[i]) + fabs(dt) * fabs(k1[i])));
         if (e > err || e != e) err = e;
     }
+    err = Coop<MODEL>::group_max(c, err);
 }
 
 // returns accepted steps; rejected attempts are added to `rejected`
@@ -211,7 +246,8 @@ SOCP_DEV void count_steps(unsigned long long *counter, int steps) {
 
 // ---- kernel: B independent trajectories ------------------------------------------------------
 #define SOCP_TRAJ_THREADS 128      // threads per CTA of the trajectory kernels
-template <int MODEL, bool ADAPTIVE>
+// L = 1: one thread per trajectory.  L = Coop<MODEL>::LANES: a cooperative group of L lanes per trajectory.
+template <int MODEL, bool ADAPTIVE, int L = 1>
 __global__ void __launch_bounds__(SOCP_TRAJ_THREADS, Model<MODEL>::MINB)
 traj_kernel(long B, int S, const double *__restrict__ mparams, const double *__restrict__ sw,
             const double *__restrict__ t0, const double *__restrict__ tf,
@@ -219,20 +255,25 @@ traj_kernel(long B, int S, const double *__restrict__ mparams, const double *__r
             double ode_tol, int *__restrict__ nsteps) {
     typedef Model<MODEL> M;
     constexpr int N = M::N;
-    long b = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long gt = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long b = gt / L;
+    const int q = (int)(threadIdx.x % L);
     int steps = 0;
     if (b < B) {
         typename M::Ctx c;
         M::load(c, mparams + b * M::NP, sw ? sw + 2 * b : nullptr);
+        if (L > 1) Coop<MODEL>::set(c, q, ((1u << L) - 1u) << ((threadIdx.x & 31) & ~(L - 1)));
         double X[N];
 #pragma unroll
         for (int i = 0; i < N; ++i) X[i] = X0[b * N + i];
         int rej = 0;
         if (ADAPTIVE) steps = compute_traj_adaptive<MODEL>(c, X, t0[b], tf[b], S, ode_tol, rej);
         else steps = compute_traj<MODEL>(c, X, t0[b], tf[b], S);
+        if (q == 0) {
 #pragma unroll
-        for (int i = 0; i < N; ++i) Xf[b * N + i] = X[i];
-        if (nsteps) { nsteps[2 * b] = steps; nsteps[2 * b + 1] = rej; }
+            for (int i = 0; i < N; ++i) Xf[b * N + i] = X[i];
+            if (nsteps) { nsteps[2 * b] = steps; nsteps[2 * b + 1] = rej; }
+        } else steps = 0;
     }
     count_steps(counter + (ADAPTIVE ? 3 : 0), steps);
 }

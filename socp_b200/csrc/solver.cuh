@@ -218,7 +218,9 @@ SOCP_DEV double fd_step(double v, double epsfcn) {
 }
 
 // ---- kernel 1: integrate every requested shooting segment --------------------------------------
-template <int MODEL, bool ADAPTIVE>
+// L lanes per work item: 1, or Coop<MODEL>::LANES (a cooperative group per segment, used when the round has too few
+// items to fill the GPU with one thread each -- the tail of a batched solve; same bits either way, integrate.cuh)
+template <int MODEL, bool ADAPTIVE, int L = 1>
 __global__ void __launch_bounds__(128, Model<MODEL>::MINB)
 integrate_worklist(SolverDev D, int cur) {
     typedef Model<MODEL> M;
@@ -232,7 +234,8 @@ integrate_worklist(SolverDev D, int cur) {
     }
     const long total = (long)nres * D.M + (long)njac * D.nJ;
     int steps = 0;
-    for (long w = (long)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += (long)gridDim.x * blockDim.x) {
+    const int cq = (int)(threadIdx.x % L);
+    for (long w = ((long)blockIdx.x * blockDim.x + threadIdx.x) / L; w < total; w += ((long)gridDim.x * blockDim.x) / L) {
         long b;
         int s, col;
         double *out;
@@ -258,6 +261,7 @@ integrate_worklist(SolverDev D, int cur) {
                       [&](int k) { int idx = nm + k; return xe[idx] + ((idx == col) ? h : 0.0); }, s, t1, t2, sw);
         typename M::Ctx c;
         M::load(c, D.mparams + b * M::NP, sw);
+        if (L > 1) Coop<MODEL>::set(c, cq, ((1u << L) - 1u) << ((threadIdx.x & 31) & ~(L - 1)));
         double X[N];
 #pragma unroll
         for (int i = 0; i < N; ++i) X[i] = xe[N * s + i];
@@ -266,14 +270,18 @@ integrate_worklist(SolverDev D, int cur) {
 #pragma unroll
             for (int i = 0; i < N; ++i) if (i == kk) X[i] += h;
         }
-        if (ADAPTIVE) { int rej = 0; steps += compute_traj_adaptive<MODEL>(c, X, t1, t2, D.S, D.ode_tol, rej); }
-        else steps += compute_traj<MODEL>(c, X, t1, t2, D.S);
+        int st;
+        if (ADAPTIVE) { int rej = 0; st = compute_traj_adaptive<MODEL>(c, X, t1, t2, D.S, D.ode_tol, rej); }
+        else st = compute_traj<MODEL>(c, X, t1, t2, D.S);
+        if (cq == 0) {
+            steps += st;
 #pragma unroll
-        for (int i = 0; i < N; ++i) out[i] = X[i];
-        int chart, stage;
-        get_chart_stage<MODEL>(c, chart, stage);
-        out[N] = (double)chart;
-        out[N + 1] = (double)stage;
+            for (int i = 0; i < N; ++i) out[i] = X[i];
+            int chart, stage;
+            get_chart_stage<MODEL>(c, chart, stage);
+            out[N] = (double)chart;
+            out[N + 1] = (double)stage;
+        }
     }
     count_steps(D.counters + (ADAPTIVE ? 3 : 0), steps);
 }

@@ -286,9 +286,15 @@ template <int MODEL>
 typename std::enable_if<!Variational<MODEL>::HAS>::type launch_variational(socp_ctx *, const SolverDev &, int, int) {}
 
 template <int MODEL>
-void launch_round(socp_ctx *ctx, const SolverDev &D, int cur, int grid_int, int grid_adv, int prof_slot) {
+void launch_round(socp_ctx *ctx, const SolverDev &D, int cur, int grid_int, int grid_adv, int prof_slot, long coop_items) {
     if (prof_slot >= 0) cudaEventRecord(prof_event(ctx, kProfEv * prof_slot), ctx->stream);
-    if (D.ode_tol > 0.) integrate_worklist<MODEL, true><<<grid_int, 128, 0, ctx->stream>>>(D, cur);
+    constexpr int L = Coop<MODEL>::LANES;
+    if (coop_items >= 0 && use_coop(ctx, coop_items, L)) {
+        // few work items (the tail of a solve, a small batch): a cooperative group of L lanes per segment
+        const int gc = (int)std::max<long>(1, std::min<long>(grid_int * (long)L, (coop_items * L + 127) / 128));
+        if (D.ode_tol > 0.) integrate_worklist<MODEL, true, L><<<gc, 128, 0, ctx->stream>>>(D, cur);
+        else integrate_worklist<MODEL, false, L><<<gc, 128, 0, ctx->stream>>>(D, cur);
+    } else if (D.ode_tol > 0.) integrate_worklist<MODEL, true><<<grid_int, 128, 0, ctx->stream>>>(D, cur);
     else integrate_worklist<MODEL, false><<<grid_int, 128, 0, ctx->stream>>>(D, cur);
     if (D.analytic) launch_variational<MODEL>(ctx, D, cur, grid_int);
     if (prof_slot >= 0) cudaEventRecord(prof_event(ctx, kProfEv * prof_slot + 1), ctx->stream);
@@ -301,13 +307,13 @@ void launch_round(socp_ctx *ctx, const SolverDev &D, int cur, int grid_int, int 
     ctx->rounds += 1;
 }
 
-void launch_round_any(socp_ctx *ctx, const SolverDev &D, int cur, int gi, int ga, int ps) {
+void launch_round_any(socp_ctx *ctx, const SolverDev &D, int cur, int gi, int ga, int ps, long coop_items) {
     switch (D.model_id) {
-    case SOCP_GODDARD: launch_round<GODDARD>(ctx, D, cur, gi, ga, ps); break;
-    case SOCP_DOUBLE_INTEGRATOR: launch_round<DOUBLE_INTEGRATOR>(ctx, D, cur, gi, ga, ps); break;
-    case SOCP_COVID19: launch_round<COVID19>(ctx, D, cur, gi, ga, ps); break;
-    case SOCP_VTOL_UAV: launch_round<VTOL_UAV>(ctx, D, cur, gi, ga, ps); break;
-    case SOCP_INTERCEPTOR: launch_round<INTERCEPTOR>(ctx, D, cur, gi, ga, ps); break;
+    case SOCP_GODDARD: launch_round<GODDARD>(ctx, D, cur, gi, ga, ps, coop_items); break;
+    case SOCP_DOUBLE_INTEGRATOR: launch_round<DOUBLE_INTEGRATOR>(ctx, D, cur, gi, ga, ps, coop_items); break;
+    case SOCP_COVID19: launch_round<COVID19>(ctx, D, cur, gi, ga, ps, coop_items); break;
+    case SOCP_VTOL_UAV: launch_round<VTOL_UAV>(ctx, D, cur, gi, ga, ps, coop_items); break;
+    case SOCP_INTERCEPTOR: launch_round<INTERCEPTOR>(ctx, D, cur, gi, ga, ps, coop_items); break;
     }
 }
 
@@ -398,7 +404,9 @@ int run_solver(socp_ctx *ctx, const socp_shape *shape, long B, const double *d_m
             const long items = live * std::max(D.nJ, D.P);                       // upper bound on work items
             const int gi = (int)std::max<long>(1, std::min<long>(grid_int, (items + 127) / 128));
             const int ga = (int)std::max<long>(1, std::min<long>(grid_adv, live));
-            launch_round_any(ctx, D, cur, gi, ga, ctx->profile ? pending : -1);
+            // `items` bounds the work items of this round (live problems only retire): the integrator may switch to
+            // cooperative groups when they cannot fill the GPU
+            launch_round_any(ctx, D, cur, gi, ga, ctx->profile ? pending : -1, items);
             if (ctx->launch_error) {                   // a launch could not be configured: nothing of this round ran
                 const int code = ctx->launch_error;
                 ctx->launch_error = 0;

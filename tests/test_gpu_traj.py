@@ -148,3 +148,22 @@ def test_full_size_properties(eng):
     assert np.max(np.abs(a - c) / np.max(np.abs(a), axis=1, keepdims=True)) <= 1e-13
     # mass only decreases, and by at most b * u_max * tf
     assert np.all(a[:, 6] <= Xi[:, 6]) and np.all(a[:, 6] >= Xi[:, 6] - 7.0 * 1.0 * 0.1 - 1e-12)
+
+
+def test_cooperative_groups_give_the_same_bits(eng):
+    """vtolUAV trajectories are integrated by a cooperative group of four lanes when the batch is small (the
+    obstacle sum split over the lanes, the adaptive error norm reduced with shuffles) and by one thread each when it
+    is large: the same trajectory gets the same bits either way, fixed-step and adaptive."""
+    import scenarios as S
+    rng = np.random.default_rng(11)
+    base = np.array([20, 8, 5, 0.3, 0.2, 0.1, -0.03, 0.013, -0.003, -0.29, 0.1, -0.03])
+    n_small, n_big = 256, 100000
+    X0 = base * (1 + 0.01 * rng.uniform(-1, 1, size=(n_big, 12)))
+    mp = np.array(S.DEFAULTS[S.VTOL])
+    small = eng.traj_batch(S.VTOL, mp, 0.0, X0[:n_small], 5.0)              # 256 x 4 lanes: cooperative groups
+    big = eng.traj_batch(S.VTOL, mp, 0.0, X0, 5.0)                          # one thread per trajectory
+    assert np.array_equal(small, big[:n_small]) and np.all(np.isfinite(small))
+    a_small, ns_small = eng.traj_adaptive_batch(S.VTOL, mp, 0.0, X0[:n_small], 5.0, 1e-6)
+    a_big, ns_big = eng.traj_adaptive_batch(S.VTOL, mp, 0.0, X0[:30000], 5.0, 1e-6)
+    assert np.array_equal(a_small, a_big[:n_small]) and np.array_equal(ns_small, ns_big[:n_small])
+    assert np.all(ns_small[:, 0] > 0)
