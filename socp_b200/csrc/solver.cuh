@@ -63,7 +63,8 @@ struct SolverDev {
     int *counts;
     unsigned long long *counters;      // [0] RK4 steps, [1] Broyden iterations, [2] Jacobian factorisations, [3] dopri steps,
                                        // [4] residual requests, [16+k] / [32+k] phase clocks
-    int jac_fast;                      // Jacobian phase: 1 = qrfac_w / qform_w + bulk copies of Q (128-thread CTA, Q in shared memory)
+    int jac_fast;                      // Jacobian phase: 1 = qrfac_w / qform_w (four lanes per column; A/B only)
+    int jac_window;                    // Jacobian phase: 1 = register-window routines when the matrix has the block structure
     int sm_count;                      // multiprocessors of the device (seq_warp)
     int phase_clocks;                  // debugging aid (SOCP_PHASE_CLOCKS=1): accumulate clock64() per phase
 };
@@ -957,6 +958,248 @@ __device__ void qform_w(int n, double *qm, int lda, double *vbuf, int rot, const
         } else if (warp == 0 && c == 0) {
             for (int e = q; e < len; e += 4) qm[(size_t)k * lda + k + e] = (e == 0) ? 1. : 0.;
         }
+        gsync<G>();
+    }
+}
+
+// ---- register-window Householder routines (block-bidiagonal + border Jacobians) ---------------------------------
+// The shooting Jacobian of a problem without free interior times is block bidiagonal (blocks of NB = 2 dim rows and
+// columns) plus a border, and Householder reflector k then spans at most the rows of TWO blocks: k .. c0(k) + W - 1,
+// c0(k) = NB (k / NB) the first column of its panel, W = 2 NB.  window_ok() checks exactly that on the matrix at hand
+// (last non-zero row of every column); when it holds, a thread can keep the W rows of ITS column that a whole panel
+// of NB reflectors can touch in registers -- static indices, everything unrolled -- instead of walking shared memory
+// one barrier-separated reflector at a time.
+//   qform_p : accumulation of Q.  Column j of Q starts as e_j and only ever sees reflectors k <= j, every column is
+//             independent of the others: NO barrier in the whole routine.  The reflectors stay where qrfac left them
+//             (shared memory, read-only here); the finished rows of a column go straight to GLOBAL memory, block of NB
+//             rows by block, so Q never passes through shared memory again.
+// Summation order: a reflector's dot product runs over the window rows kk .. W-1 with four running sums ((t - kk) & 3);
+// rows past the reflector's last non-zero row add exact zeros.  Same values as qform_g up to the association of the
+// last partial group of four (qform_g sends a tail of up to three elements to its first sum).
+template <int G>
+SOCP_DEV bool window_ok(int n, int NB, const int *hi, int *flag) {
+    const int tid = threadIdx.x % G;
+    if (tid == 0) *flag = 1;
+    gsync<G>();
+    for (int k = tid; k < n; k += G)
+        if (max(hi[k], k) >= (k / NB) * NB + 2 * NB) *flag = 0;
+    gsync<G>();
+    return *flag != 0;
+}
+
+// dot4 over the window: sum_{i < len} x[i] y[i] with dot4's association (four running sums over complete groups of four,
+// the incomplete last group on the first sum).  x(t), y(t) give element t of the window (static t), kk is the window
+// index of element 0; `len` is uniform over the threads, so the branches are uniform too.
+#define SOCP_WIN_DOT4(W, kk, len, X, Y, sum)                                                      \
+    do {                                                                                          \
+        double s0_ = 0., s1_ = 0., s2_ = 0., s3_ = 0.;                                            \
+        _Pragma("unroll") for (int g_ = 0; g_ < ((W) - (kk) + 3) / 4; ++g_) {                      \
+            const int t_ = (kk) + 4 * g_;                                                         \
+            if (4 * g_ + 3 < (len)) {                                                             \
+                if (t_ + 3 < (W)) {                                                               \
+                    s0_ = fma(X(t_), Y(t_), s0_); s1_ = fma(X(t_ + 1), Y(t_ + 1), s1_);           \
+                    s2_ = fma(X(t_ + 2), Y(t_ + 2), s2_); s3_ = fma(X(t_ + 3), Y(t_ + 3), s3_);   \
+                }                                                                                 \
+            } else {                                                                              \
+                if (4 * g_ < (len) && t_ < (W)) s0_ = fma(X(t_), Y(t_), s0_);                     \
+                if (4 * g_ + 1 < (len) && t_ + 1 < (W)) s0_ = fma(X(t_ + 1), Y(t_ + 1), s0_);     \
+                if (4 * g_ + 2 < (len) && t_ + 2 < (W)) s0_ = fma(X(t_ + 2), Y(t_ + 2), s0_);     \
+            }                                                                                     \
+        }                                                                                         \
+        (sum) = (s0_ + s1_) + (s2_ + s3_);                                                        \
+    } while (0)
+
+template <int G, int NB>
+__device__ void qform_p(int n, const double *a, int lda, const int *hi, double *gq) {
+    constexpr int W = 2 * NB;
+    const int j = threadIdx.x % G;                 // this thread's column of Q
+    if (j >= n) return;
+    int p = j / NB;
+    double c[W];
+#pragma unroll
+    for (int t = 0; t < W; ++t) c[t] = (t == j - p * NB) ? 1. : 0.;
+    double *out = gq + (size_t)j * n;
+    // rows below the first window are zeros of e_j for good
+    for (int r = p * NB + W; r < n; ++r) out[r] = 0.;
+    for (; p >= 0; --p) {
+        const int c0 = p * NB;
+        // reflectors of this panel that act on column j: k = min(j, c0 + NB - 1) .. c0, highest first
+#pragma unroll
+        for (int kk = NB - 1; kk >= 0; --kk) {
+            const int k = c0 + kk;
+            if (k > j || k >= n) continue;
+            const double *v = a + (size_t)k * lda + c0;        // v[t] = reflector k at row c0 + t (t >= kk)
+            const double wk = v[kk];
+            if (wk == 0.) continue;                            // the identity
+            const int len = max(hi[k], k) - k + 1;             // rows k .. hk; exact zeros below
+#define SOCP_CX(t) c[t]
+#define SOCP_VX(t) v[t]
+            double sum;
+            SOCP_WIN_DOT4(W, kk, len, SOCP_CX, SOCP_VX, sum);
+            if (sum != 0.) {
+                const double temp = sum / wk;
+#pragma unroll
+                for (int t = kk; t < W; ++t) if (t - kk < len) c[t] = __fma_rn(-temp, v[t], c[t]);
+            }
+        }
+        // rows c0 + NB .. c0 + W - 1 are final (lower panels stop at row c0 + NB - 1): out they go, and the window moves up
+#pragma unroll
+        for (int t = NB; t < W; ++t) if (c0 + t < n) out[c0 + t] = c[t];
+        if (p == 0) {
+#pragma unroll
+            for (int t = 0; t < NB; ++t) if (t < n) out[t] = c[t];
+        } else {
+#pragma unroll
+            for (int t = W - 1; t >= NB; --t) c[t] = c[t - NB];
+#pragma unroll
+            for (int t = 0; t < NB; ++t) c[t] = 0.;
+        }
+    }
+}
+
+// MINPACK enorm of the window elements x[kk .. kk + len) by ONE thread, bit for bit enorm_warp(len, .) for len <= 32:
+// element i plays lane i, the butterfly 16, 8, 4, 2, 1 is evaluated as the binary tree it is.
+template <int W>
+SOCP_DEV double enorm_win(const double (&c)[W], int kk, int len) {
+    const double rdwarf = 3.834e-20, rgiant = 1.304e19;
+    const double dn = (double)len;
+    double sq[32];
+    double small_max = 0., big_max = 0.;
+    bool isnan_ = false;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        double s2 = 0.;
+        if (i < W) {
+            // kk is a loop constant of the (unrolled) caller, i is static: c[kk + i] is a register
+            const double xabs = (i < len && kk + i < W) ? fabs(c[(kk + i < W) ? kk + i : 0]) : 0.;
+            if (i < len) {
+                if (xabs > rdwarf && xabs * dn < rgiant) s2 = fma(xabs, xabs, 0.);
+                else if (xabs <= rdwarf) small_max = fmax(small_max, xabs);
+                else if (xabs == xabs) big_max = fmax(big_max, xabs);
+                else isnan_ = true;
+            }
+        }
+        sq[i] = s2;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+        for (int i = 0; i < off; ++i) sq[i] = sq[i] + sq[i + off];
+    }
+    const double s2 = sq[0];
+    if (isnan_) return s2 + nan("");
+    if (small_max == 0. && big_max == 0.) return sqrt(s2);
+    // badly scaled column: MINPACK's scaled sums (same association as enorm_warp: lane partials, then the tree)
+    const double x1max = big_max, x3max = small_max;
+    double p1[32], p3[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        p1[i] = 0.; p3[i] = 0.;
+        if (i < W && i < len && kk + i < W) {
+            const double xabs = fabs(c[(kk + i < W) ? kk + i : 0]);
+            if (!(xabs > rdwarf && xabs * dn < rgiant)) {
+                if (xabs <= rdwarf) { if (xabs != 0.) { const double q = xabs / x3max; p3[i] = fma(q, q, 0.); } }
+                else { const double q = xabs / x1max; p1[i] = fma(q, q, 0.); }
+            }
+        }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+        for (int i = 0; i < off; ++i) { p1[i] = p1[i] + p1[i + off]; p3[i] = p3[i] + p3[i + off]; }
+    }
+    const double s1 = p1[0], s3 = p3[0];
+    if (s1 != 0.) return x1max * sqrt(s1 + (s2 / x1max) / x1max);
+    if (s2 != 0.) {
+        if (s2 >= x3max) return sqrt(s2 * (1. + (x3max / s2) * (x3max * s3)));
+        return sqrt(x3max * ((s2 / x3max) + (x3max * s3)));
+    }
+    return x3max * sqrt(s3);
+}
+
+//   qrfac_p : the factorisation itself, a panel of NB reflectors at a time.  Thread k holds the W window rows of
+//             column k (the columns c0 .. n-1 of the panel and to its right, and Q^T f as column n) in registers for the
+//             whole panel.  A step: the owner of column j forms the norm of its sub-column alone (registers, no
+//             reduction) and publishes the raw sub-column; len threads scale one element each (the divides run in
+//             parallel); every column to the right applies the reflector to its window.  Two barriers per reflector
+//             and no pass over shared memory besides the published reflector (old form: three barriers, every operand
+//             through shared memory).  Bit for bit the factors of qrfac_g.
+// pub: [2][W + 2] doubles of shared memory (raw / scaled reflector; slots W, W + 1: norm and the "non-zero" flag).
+template <int G, int NB>
+__device__ void qrfac_p(int n, double *a, int lda, double *rdiag, double *acnorm, double *qtf, double *pub, int *hi) {
+    constexpr int W = 2 * NB;
+    const int tid = threadIdx.x % G, lane = tid & 31;
+    gsync<G>();
+    for (int j = tid >> 5; j < n; j += G / 32) {       // column norms, one warp per column
+        const double v = enorm_warp(n, a + (size_t)j * lda);
+        if (lane == 0) acnorm[j] = v;
+    }
+    for (int k = tid; k <= n; k += G) {                // last non-zero row of every column (qtf: dense)
+        int last = (k < n) ? 0 : n - 1;
+        if (k < n) {
+            const double *ck = a + (size_t)k * lda;
+            for (int i = n - 1; i > 0; --i) if (ck[i] != 0.) { last = i; break; }
+        }
+        hi[k] = last;
+    }
+    gsync<G>();
+    const int npan = (n + NB - 1) / NB;
+    for (int p = 0; p < npan; ++p) {
+        const int c0 = p * NB;
+        const int k = c0 + tid;                        // this thread's column (k == n: Q^T f); idle beyond
+        const bool mine = k <= n;
+        double *col = (k < n) ? a + (size_t)k * lda : qtf;
+        double c[W];
+#pragma unroll
+        for (int t = 0; t < W; ++t) c[t] = (mine && c0 + t < n) ? col[c0 + t] : 0.;
+#pragma unroll
+        for (int jj = 0; jj < NB; ++jj) {
+            const int j = c0 + jj;
+            if (j >= n) break;                         // uniform
+            double *raw = pub + (size_t)(jj & 1) * (W + 2);
+            if (tid == jj) {                           // the owner of column j
+                // hi[j] is this thread's own entry (it alone updates it, when a reflector fills its column): nobody
+                // else may read it before the barrier, so the span travels with the published sub-column
+                const int len_own = max(hi[j], j) - j + 1;
+                double ajnorm = enorm_win<W>(c, jj, len_own);
+                if (ajnorm != 0. && c[jj] < 0.) ajnorm = -ajnorm;
+#pragma unroll
+                for (int t = jj; t < W; ++t) raw[t] = c[t];
+                raw[W] = ajnorm;
+                raw[W + 1] = (double)len_own;
+                rdiag[j] = -ajnorm;
+            }
+            gsync<G>();
+            const double ajnorm = raw[W];
+            const int len = (int)raw[W + 1], hj = j + len - 1;
+            if (ajnorm != 0.) {                        // uniform
+                // scaling: one element per thread (the same divide the thread-per-row loop of qrfac_g does)
+                if (tid < len) {
+                    double v = raw[jj + tid] / ajnorm;
+                    if (tid == 0) v += 1.;
+                    raw[jj + tid] = v;
+                }
+                gsync<G>();
+                if (tid == jj) {
+#pragma unroll
+                    for (int t = jj; t < W; ++t) if (t - jj < len) c[t] = raw[t];
+                } else if (mine && tid > jj) {
+                    const double ajj = raw[jj];
+#define SOCP_RX(t) raw[t]
+                    double sum;
+                    SOCP_WIN_DOT4(W, jj, len, SOCP_RX, SOCP_CX, sum);
+                    if (sum != 0.) {
+                        const double temp = sum / ajj;
+#pragma unroll
+                        for (int t = jj; t < W; ++t) if (t - jj < len) c[t] = __fma_rn(-temp, raw[t], c[t]);
+                        if (hi[k] < hj) hi[k] = hj;
+                    }
+                }
+            }
+        }
+        // windows back to shared memory; the next panel's columns read rows c0 + NB .. from there
+#pragma unroll
+        for (int t = 0; t < W; ++t) if (mine && c0 + t < n) col[c0 + t] = c[t];
         gsync<G>();
     }
 }
@@ -1932,7 +2175,7 @@ hybrd_chain_kernel(SolverDev D, int cur, int per_group_doubles) {
 
 // ---- kernel 2c: problems whose forward-difference Jacobian arrived ------------------------------
 template <int G, bool STAGE_R, bool STAGE_Q>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 3)      // three CTAs per SM is what shared memory allows at P = 85: 168 registers
 hybrd_jac_kernel(SolverDev D, int cur, int per_group_doubles) {
     const int GROUPS = (G == 32) ? (int)(blockDim.x >> 5) : 1;
     const int grp = (G == 32) ? (threadIdx.x >> 5) : 0;
@@ -2006,7 +2249,24 @@ hybrd_jac_kernel(SolverDev D, int cur, int per_group_doubles) {
         for (int i = tid; i < n; i += G) W.qtf[i] = W.fvec[i];
         // wa1 = rdiag, wa2 = acnorm
         int *hi = (int *)W.scr;                            // [n + 1] last non-zero row per column (scr is free here)
-        if (fast) qrfac_w<G>(n, W.q, W.ldq, W.wa1, W.wa2, W.qtf, vbuf, seq_warp<G>(D.sm_count), hi);
+        // Register-window routines when the Jacobian at hand has the block-bidiagonal + border structure (every
+        // sub-column fits the two-block window; fill-in stays inside it): decided per matrix, from its own zeros.
+        bool win = false;
+        // (instantiated for the layout the 32 < P <= ~150 problems run with -- Q staged, R in global memory -- and the
+        // block sizes of the shipped models with a multi-segment demo: 14 goddard, 12 vtolUAV / doubleIntegrator)
+        if ((G == 128) && STAGE_Q && !STAGE_R && D.jac_window && (D.N == 14 || D.N == 12) && n < G) {
+            for (int k = tid; k < n; k += G) {
+                const double *ck = W.q + (size_t)k * W.ldq;
+                int last = 0;
+                for (int i = n - 1; i > 0; --i) if (ck[i] != 0.) { last = i; break; }
+                hi[k] = last;
+            }
+            win = window_ok<G>(n, D.N, hi, (int *)red);
+        }
+        if ((G == 128) && STAGE_Q && !STAGE_R && win) {
+            if (D.N == 14) qrfac_p<G, 14>(n, W.q, W.ldq, W.wa1, W.wa2, W.qtf, vbuf, hi);
+            else qrfac_p<G, 12>(n, W.q, W.ldq, W.wa1, W.wa2, W.qtf, vbuf, hi);
+        } else if (fast) qrfac_w<G>(n, W.q, W.ldq, W.wa1, W.wa2, W.qtf, vbuf, seq_warp<G>(D.sm_count), hi);
         else qrfac_g<G>(n, W.q, W.ldq, W.wa1, W.wa2, W.qtf, red, seq_warp<G>(D.sm_count), hi);
         SOCP_PHASE(32, 1);
         if (is[I_ITER] == 1) {
@@ -2025,7 +2285,15 @@ hybrd_jac_kernel(SolverDev D, int cur, int per_group_doubles) {
         }
         pack_r_g<G>(n, W.q, W.ldq, W.wa1, W.r);
         SOCP_PHASE(32, 2);
-        if (fast) qform_w<G>(n, W.q, W.ldq, vbuf, seq_warp<G>(D.sm_count), hi);
+        // register-window accumulation of Q when every reflector fits the two-block window (checked on this matrix):
+        // no barrier, Q goes straight to global memory
+        bool q_in_global = false;
+        if ((G == 128) && STAGE_Q && !STAGE_R && win) {
+            if (D.N == 14) qform_p<G, 14>(n, W.q, W.ldq, hi, gq);
+            else qform_p<G, 12>(n, W.q, W.ldq, hi, gq);
+            gsync<G>();
+            q_in_global = true;
+        } else if (fast) qform_w<G>(n, W.q, W.ldq, vbuf, seq_warp<G>(D.sm_count), hi);
         else qform_g<G>(n, W.q, W.ldq, W.wa1, seq_warp<G>(D.sm_count), hi);
         SOCP_PHASE(32, 3);
         for (int j = tid; j < n; j += G) W.diag[j] = fmax(W.diag[j], W.wa2[j]);
@@ -2036,7 +2304,9 @@ hybrd_jac_kernel(SolverDev D, int cur, int per_group_doubles) {
         gcopy<G>(D.qtf + b * n, W.qtf, n); gcopy<G>(D.wa1 + b * n, W.wa1, n);
         if (STAGE_R) gcopy<G>(D.r + (size_t)b * D.LRS, W.r, D.LR);
         SOCP_PHASE(32, 5);
-        if (bulk) {
+        if (q_in_global) {
+            // qform_p wrote Q to global memory column by column
+        } else if (bulk) {
             // the accumulated Q leaves with one bulk copy; the next problem's copy in waits for it to have read the buffer
             fence_async_smem();
             gsync<G>();

@@ -374,6 +374,9 @@ int run_solver(socp_ctx *ctx, const socp_shape *shape, long B, const double *d_m
         // bits, measured SLOWER than the thread-per-column ones: 1074 vs 785 ms per step -- kept for A/B runs)
         const char *jm = getenv("SOCP_JAC");
         D.jac_fast = (jm && !strcmp(jm, "lanes4")) ? 1 : 0;
+        // SOCP_JAC=old: the barrier-per-reflector routines everywhere (A/B runs); default: register-window routines
+        // wherever the Jacobian has the block-bidiagonal + border structure
+        D.jac_window = (jm && (!strcmp(jm, "old") || !strcmp(jm, "lanes4"))) ? 0 : 1;
     }
     const int grid_int = ctx->sm_count * 8;
     const int grid_adv = ctx->sm_count * 6;
