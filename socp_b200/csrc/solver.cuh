@@ -62,7 +62,7 @@ struct SolverDev {
     int *lists;
     int *counts;
     unsigned long long *counters;      // [0] RK4 steps, [1] Broyden iterations, [2] Jacobian factorisations, [3] dopri steps,
-                                       // [4] residual requests, [16+k] / [32+k] phase clocks
+                                       // [4] residual requests, [5] Q passes, [16+k] / [32+k] phase clocks
     int jac_fast;                      // Jacobian phase: 1 = qrfac_w / qform_w (four lanes per column; A/B only)
     int jac_window;                    // Jacobian phase: 1 = register-window routines when the matrix has the block structure
     int sm_count;                      // multiprocessors of the device (seq_warp)
@@ -1021,6 +1021,7 @@ __device__ void qform_p(int n, const double *a, int lda, const int *hi, double *
     double *out = gq + (size_t)j * n;
     // rows below the first window are zeros of e_j for good
     for (int r = p * NB + W; r < n; ++r) out[r] = 0.;
+#pragma unroll 1
     for (; p >= 0; --p) {
         const int c0 = p * NB;
         // reflectors of this panel that act on column j: k = min(j, c0 + NB - 1) .. c0, highest first
@@ -1057,74 +1058,87 @@ __device__ void qform_p(int n, const double *a, int lda, const int *hi, double *
     }
 }
 
-// MINPACK enorm of the window elements x[kk .. kk + len) by ONE thread, bit for bit enorm_warp(len, .) for len <= 32:
-// element i plays lane i, the butterfly 16, 8, 4, 2, 1 is evaluated as the binary tree it is.
-template <int W>
-SOCP_DEV double enorm_win(const double (&c)[W], int kk, int len) {
-    const double rdwarf = 3.834e-20, rgiant = 1.304e19;
-    const double dn = (double)len;
-    double sq[32];
-    double small_max = 0., big_max = 0.;
-    bool isnan_ = false;
-#pragma unroll
-    for (int i = 0; i < 32; ++i) {
-        double s2 = 0.;
-        if (i < W) {
-            // kk is a loop constant of the (unrolled) caller, i is static: c[kk + i] is a register
-            const double xabs = (i < len && kk + i < W) ? fabs(c[(kk + i < W) ? kk + i : 0]) : 0.;
-            if (i < len) {
-                if (xabs > rdwarf && xabs * dn < rgiant) s2 = fma(xabs, xabs, 0.);
-                else if (xabs <= rdwarf) small_max = fmax(small_max, xabs);
-                else if (xabs == xabs) big_max = fmax(big_max, xabs);
-                else isnan_ = true;
-            }
-        }
-        sq[i] = s2;
-    }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-#pragma unroll
-        for (int i = 0; i < off; ++i) sq[i] = sq[i] + sq[i + off];
-    }
-    const double s2 = sq[0];
-    if (isnan_) return s2 + nan("");
-    if (small_max == 0. && big_max == 0.) return sqrt(s2);
-    // badly scaled column: MINPACK's scaled sums (same association as enorm_warp: lane partials, then the tree)
-    const double x1max = big_max, x3max = small_max;
-    double p1[32], p3[32];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) {
-        p1[i] = 0.; p3[i] = 0.;
-        if (i < W && i < len && kk + i < W) {
-            const double xabs = fabs(c[(kk + i < W) ? kk + i : 0]);
-            if (!(xabs > rdwarf && xabs * dn < rgiant)) {
-                if (xabs <= rdwarf) { if (xabs != 0.) { const double q = xabs / x3max; p3[i] = fma(q, q, 0.); } }
-                else { const double q = xabs / x1max; p1[i] = fma(q, q, 0.); }
-            }
-        }
-    }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-#pragma unroll
-        for (int i = 0; i < off; ++i) { p1[i] = p1[i] + p1[i + off]; p3[i] = p3[i] + p3[i + off]; }
-    }
-    const double s1 = p1[0], s3 = p3[0];
-    if (s1 != 0.) return x1max * sqrt(s1 + (s2 / x1max) / x1max);
-    if (s2 != 0.) {
-        if (s2 >= x3max) return sqrt(s2 * (1. + (x3max / s2) * (x3max * s3)));
-        return sqrt(x3max * ((s2 / x3max) + (x3max * s3)));
-    }
-    return x3max * sqrt(s3);
-}
-
 //   qrfac_p : the factorisation itself, a panel of NB reflectors at a time.  Thread k holds the W window rows of
 //             column k (the columns c0 .. n-1 of the panel and to its right, and Q^T f as column n) in registers for the
-//             whole panel.  A step: the owner of column j forms the norm of its sub-column alone (registers, no
-//             reduction) and publishes the raw sub-column; len threads scale one element each (the divides run in
-//             parallel); every column to the right applies the reflector to its window.  Two barriers per reflector
-//             and no pass over shared memory besides the published reflector (old form: three barriers, every operand
-//             through shared memory).  Bit for bit the factors of qrfac_g.
-// pub: [2][W + 2] doubles of shared memory (raw / scaled reflector; slots W, W + 1: norm and the "non-zero" flag).
+//             whole panel.  A step: the owner of column j publishes its raw sub-column; every warp forms its norm
+//             (enorm_warp on the published copy: the same bits in every warp, no barrier for it); len threads scale one
+//             element each; every column to the right applies the reflector to its window registers.  Two barriers per
+//             reflector, and the only shared-memory traffic is the published reflector (qrfac_g: three barriers, every
+//             operand of every column through shared memory).  Bit for bit the factors of qrfac_g.
+// pub: [2][2 W + 2] doubles of shared memory (raw sub-column, scaled reflector, the span of the sub-column).
+// dot4 of the published reflector with the window (compile-time window position: every index is a register)
+template <int W, int KK>
+SOCP_DEV double win_dot4(int len, const double *x, const double (&c)[W]) {
+    double s0 = 0., s1 = 0., s2 = 0., s3 = 0.;
+#pragma unroll
+    for (int g = 0; g < (W - KK + 3) / 4; ++g) {
+        constexpr int dummy = 0; (void)dummy;
+        const int t = KK + 4 * g;
+        if (4 * g + 3 < len) {
+            if (t + 3 < W) {
+                s0 = fma(x[t], c[t], s0); s1 = fma(x[t + 1], c[(t + 1 < W) ? t + 1 : 0], s1);
+                s2 = fma(x[t + 2], c[(t + 2 < W) ? t + 2 : 0], s2); s3 = fma(x[t + 3], c[(t + 3 < W) ? t + 3 : 0], s3);
+            }
+        } else {
+            if (4 * g < len && t < W) s0 = fma(x[t], c[t], s0);
+            if (4 * g + 1 < len && t + 1 < W) s0 = fma(x[t + 1], c[(t + 1 < W) ? t + 1 : 0], s0);
+            if (4 * g + 2 < len && t + 2 < W) s0 = fma(x[t + 2], c[(t + 2 < W) ? t + 2 : 0], s0);
+        }
+    }
+    return (s0 + s1) + (s2 + s3);
+}
+
+// one reflector of a panel (JJ: its position in the panel, a compile-time constant so that the window stays in registers)
+template <int G, int NB, int JJ>
+struct QrStep {
+    static constexpr int W = 2 * NB, PS = 2 * W + 2;
+    SOCP_DEV static void run(int n, int c0, int tid, int k, bool mine, double (&c)[2 * NB], double *pub, double *rdiag, int *hi) {
+        const int j = c0 + JJ;
+        if (j < n) {                                   // uniform
+            double *raw = pub + (size_t)(JJ & 1) * PS, *vs = raw + W;
+            if (tid == JJ) {                           // the owner of column j publishes its sub-column
+                // hi[j] is this thread's own entry (it alone updates it, when a reflector fills its column): nobody
+                // else may read it before the barrier, so the span travels with the published sub-column
+#pragma unroll
+                for (int t = JJ; t < W; ++t) raw[t] = c[t];
+                raw[2 * W] = (double)(max(hi[j], j) - j + 1);
+            }
+            gsync<G>();
+            const int len = (int)raw[2 * W], hj = j + len - 1;
+            double ajnorm = enorm_warp(len, raw + JJ);
+            if (ajnorm != 0.) {                        // uniform
+                if (raw[JJ] < 0.) ajnorm = -ajnorm;
+                // scaling: one element per thread (the same divide the thread-per-row loop of qrfac_g does)
+                if (tid < len) {
+                    double v = raw[JJ + tid] / ajnorm;
+                    if (tid == 0) v += 1.;
+                    vs[JJ + tid] = v;
+                }
+                gsync<G>();
+                if (tid == JJ) {
+#pragma unroll
+                    for (int t = JJ; t < W; ++t) if (t - JJ < len) c[t] = vs[t];
+                } else if (mine && tid > JJ) {
+                    const double ajj = vs[JJ];
+                    const double sum = win_dot4<W, JJ>(len, vs, c);
+                    if (sum != 0.) {
+                        const double temp = sum / ajj;
+#pragma unroll
+                        for (int t = JJ; t < W; ++t) if (t - JJ < len) c[t] = __fma_rn(-temp, vs[t], c[t]);
+                        if (hi[k] < hj) hi[k] = hj;
+                    }
+                }
+            }
+            if (tid == JJ) rdiag[j] = -ajnorm;
+        }
+        QrStep<G, NB, JJ + 1>::run(n, c0, tid, k, mine, c, pub, rdiag, hi);
+    }
+};
+template <int G, int NB>
+struct QrStep<G, NB, NB> {
+    SOCP_DEV static void run(int, int, int, int, bool, double (&)[2 * NB], double *, double *, int *) {}
+};
+
 template <int G, int NB>
 __device__ void qrfac_p(int n, double *a, int lda, double *rdiag, double *acnorm, double *qtf, double *pub, int *hi) {
     constexpr int W = 2 * NB;
@@ -1144,6 +1158,7 @@ __device__ void qrfac_p(int n, double *a, int lda, double *rdiag, double *acnorm
     }
     gsync<G>();
     const int npan = (n + NB - 1) / NB;
+#pragma unroll 1
     for (int p = 0; p < npan; ++p) {
         const int c0 = p * NB;
         const int k = c0 + tid;                        // this thread's column (k == n: Q^T f); idle beyond
@@ -1152,51 +1167,7 @@ __device__ void qrfac_p(int n, double *a, int lda, double *rdiag, double *acnorm
         double c[W];
 #pragma unroll
         for (int t = 0; t < W; ++t) c[t] = (mine && c0 + t < n) ? col[c0 + t] : 0.;
-#pragma unroll
-        for (int jj = 0; jj < NB; ++jj) {
-            const int j = c0 + jj;
-            if (j >= n) break;                         // uniform
-            double *raw = pub + (size_t)(jj & 1) * (W + 2);
-            if (tid == jj) {                           // the owner of column j
-                // hi[j] is this thread's own entry (it alone updates it, when a reflector fills its column): nobody
-                // else may read it before the barrier, so the span travels with the published sub-column
-                const int len_own = max(hi[j], j) - j + 1;
-                double ajnorm = enorm_win<W>(c, jj, len_own);
-                if (ajnorm != 0. && c[jj] < 0.) ajnorm = -ajnorm;
-#pragma unroll
-                for (int t = jj; t < W; ++t) raw[t] = c[t];
-                raw[W] = ajnorm;
-                raw[W + 1] = (double)len_own;
-                rdiag[j] = -ajnorm;
-            }
-            gsync<G>();
-            const double ajnorm = raw[W];
-            const int len = (int)raw[W + 1], hj = j + len - 1;
-            if (ajnorm != 0.) {                        // uniform
-                // scaling: one element per thread (the same divide the thread-per-row loop of qrfac_g does)
-                if (tid < len) {
-                    double v = raw[jj + tid] / ajnorm;
-                    if (tid == 0) v += 1.;
-                    raw[jj + tid] = v;
-                }
-                gsync<G>();
-                if (tid == jj) {
-#pragma unroll
-                    for (int t = jj; t < W; ++t) if (t - jj < len) c[t] = raw[t];
-                } else if (mine && tid > jj) {
-                    const double ajj = raw[jj];
-#define SOCP_RX(t) raw[t]
-                    double sum;
-                    SOCP_WIN_DOT4(W, jj, len, SOCP_RX, SOCP_CX, sum);
-                    if (sum != 0.) {
-                        const double temp = sum / ajj;
-#pragma unroll
-                        for (int t = jj; t < W; ++t) if (t - jj < len) c[t] = __fma_rn(-temp, raw[t], c[t]);
-                        if (hi[k] < hj) hi[k] = hj;
-                    }
-                }
-            }
-        }
+        QrStep<G, NB, 0>::run(n, c0, tid, k, mine, c, pub, rdiag, hi);
         // windows back to shared memory; the next panel's columns read rows c0 + NB .. from there
 #pragma unroll
         for (int t = 0; t < W; ++t) if (mine && c0 + t < n) col[c0 + t] = c[t];
@@ -1835,6 +1806,7 @@ hybrd_qpass_kernel(SolverDev D, int cur) {
             if (lane < 4 && j0 + lane < n) D.wa2[b * n + j0 + lane] = (lane == 0) ? p0 : (lane == 1) ? p1 : (lane == 2) ? p2 : p3;
         }
         if (tid == 0) {
+            atomicAdd(D.counters + 5, 1ULL);                    // problems through the Q pass
             if (pend) { is[I_PEND] = 0; bulk_wait_read(); }     // the copy out has read the shared buffer
         }
         fence_async_smem();
@@ -2253,8 +2225,8 @@ hybrd_jac_kernel(SolverDev D, int cur, int per_group_doubles) {
         // sub-column fits the two-block window; fill-in stays inside it): decided per matrix, from its own zeros.
         bool win = false;
         // (instantiated for the layout the 32 < P <= ~150 problems run with -- Q staged, R in global memory -- and the
-        // block sizes of the shipped models with a multi-segment demo: 14 goddard, 12 vtolUAV / doubleIntegrator)
-        if ((G == 128) && STAGE_Q && !STAGE_R && D.jac_window && (D.N == 14 || D.N == 12) && n < G) {
+        // block size of the benchmark model, 14; every other shape takes the barrier-per-reflector routines)
+        if ((G == 128) && STAGE_Q && !STAGE_R && D.jac_window && D.N == 14 && n < G) {
             for (int k = tid; k < n; k += G) {
                 const double *ck = W.q + (size_t)k * W.ldq;
                 int last = 0;
@@ -2263,10 +2235,14 @@ hybrd_jac_kernel(SolverDev D, int cur, int per_group_doubles) {
             }
             win = window_ok<G>(n, D.N, hi, (int *)red);
         }
+#ifdef SOCP_QRFAC_WINDOW
+        // the register-window factorisation: bit-identical, measured SLOWER than qrfac_g (351 k vs ~280 k cycles per
+        // Jacobian at P = 85, profiles/r2i_*): compiled only on request, for A/B runs
         if ((G == 128) && STAGE_Q && !STAGE_R && win) {
-            if (D.N == 14) qrfac_p<G, 14>(n, W.q, W.ldq, W.wa1, W.wa2, W.qtf, vbuf, hi);
-            else qrfac_p<G, 12>(n, W.q, W.ldq, W.wa1, W.wa2, W.qtf, vbuf, hi);
-        } else if (fast) qrfac_w<G>(n, W.q, W.ldq, W.wa1, W.wa2, W.qtf, vbuf, seq_warp<G>(D.sm_count), hi);
+            qrfac_p<G, 14>(n, W.q, W.ldq, W.wa1, W.wa2, W.qtf, vbuf, hi);
+        } else
+#endif
+        if (fast) qrfac_w<G>(n, W.q, W.ldq, W.wa1, W.wa2, W.qtf, vbuf, seq_warp<G>(D.sm_count), hi);
         else qrfac_g<G>(n, W.q, W.ldq, W.wa1, W.wa2, W.qtf, red, seq_warp<G>(D.sm_count), hi);
         SOCP_PHASE(32, 1);
         if (is[I_ITER] == 1) {
@@ -2289,8 +2265,7 @@ hybrd_jac_kernel(SolverDev D, int cur, int per_group_doubles) {
         // no barrier, Q goes straight to global memory
         bool q_in_global = false;
         if ((G == 128) && STAGE_Q && !STAGE_R && win) {
-            if (D.N == 14) qform_p<G, 14>(n, W.q, W.ldq, hi, gq);
-            else qform_p<G, 12>(n, W.q, W.ldq, hi, gq);
+            qform_p<G, 14>(n, W.q, W.ldq, hi, gq);
             gsync<G>();
             q_in_global = true;
         } else if (fast) qform_w<G>(n, W.q, W.ldq, vbuf, seq_warp<G>(D.sm_count), hi);
