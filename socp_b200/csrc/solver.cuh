@@ -2163,7 +2163,11 @@ hybrd_jac_kernel(SolverDev D, int cur, int per_group_doubles) {
     const int ldq_s = n | 1;                               // odd leading dimension in shared memory
     // fast form (128-thread CTA, Q staged): Q travels by bulk copy when its shared layout equals the global
     // one (odd P), the reflector buffers of qrfac_w / qform_w follow Q in shared memory
-    const bool fast = (G == 128) && STAGE_Q && D.jac_fast;
+#ifdef SOCP_JAC_LANES4
+    const bool fast = (G == 128) && STAGE_Q && D.jac_fast;      // A/B build only: four lanes per column (measured slower)
+#else
+    constexpr bool fast = false;
+#endif
     const bool bulk = (G == 128) && STAGE_Q && ldq_s == n;
     __shared__ unsigned long long jac_bar;
     unsigned jac_parity = 0;
@@ -2242,8 +2246,11 @@ hybrd_jac_kernel(SolverDev D, int cur, int per_group_doubles) {
             qrfac_p<G, 14>(n, W.q, W.ldq, W.wa1, W.wa2, W.qtf, vbuf, hi);
         } else
 #endif
+#ifdef SOCP_JAC_LANES4
         if (fast) qrfac_w<G>(n, W.q, W.ldq, W.wa1, W.wa2, W.qtf, vbuf, seq_warp<G>(D.sm_count), hi);
-        else qrfac_g<G>(n, W.q, W.ldq, W.wa1, W.wa2, W.qtf, red, seq_warp<G>(D.sm_count), hi);
+        else
+#endif
+        qrfac_g<G>(n, W.q, W.ldq, W.wa1, W.wa2, W.qtf, red, seq_warp<G>(D.sm_count), hi);
         SOCP_PHASE(32, 1);
         if (is[I_ITER] == 1) {
             for (int j = tid; j < n; j += G) {
@@ -2268,7 +2275,10 @@ hybrd_jac_kernel(SolverDev D, int cur, int per_group_doubles) {
             qform_p<G, 14>(n, W.q, W.ldq, hi, gq);
             gsync<G>();
             q_in_global = true;
-        } else if (fast) qform_w<G>(n, W.q, W.ldq, vbuf, seq_warp<G>(D.sm_count), hi);
+        }
+#ifdef SOCP_JAC_LANES4
+        else if (fast) qform_w<G>(n, W.q, W.ldq, vbuf, seq_warp<G>(D.sm_count), hi);
+#endif
         else qform_g<G>(n, W.q, W.ldq, W.wa1, seq_warp<G>(D.sm_count), hi);
         SOCP_PHASE(32, 3);
         for (int j = tid; j < n; j += G) W.diag[j] = fmax(W.diag[j], W.wa2[j]);

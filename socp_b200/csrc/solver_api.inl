@@ -370,8 +370,8 @@ int run_solver(socp_ctx *ctx, const socp_shape *shape, long B, const double *d_m
     D.sm_count = ctx->sm_count;
     D.phase_clocks = getenv("SOCP_PHASE_CLOCKS") ? 1 : 0;
     {
-        // SOCP_JAC=lanes4: the one-barrier, four-lanes-per-column Householder routines (qrfac_w / qform_w; same
-        // bits, measured SLOWER than the thread-per-column ones: 1074 vs 785 ms per step -- kept for A/B runs)
+        // SOCP_JAC=lanes4 (builds with -DSOCP_JAC_LANES4 only): the one-barrier, four-lanes-per-column Householder
+        // routines (qrfac_w / qform_w; same bits, measured SLOWER than the thread-per-column ones: 1074 vs 785 ms per step)
         const char *jm = getenv("SOCP_JAC");
         D.jac_fast = (jm && !strcmp(jm, "lanes4")) ? 1 : 0;
         // SOCP_JAC=old: the barrier-per-reflector routines everywhere (A/B runs); default: register-window routines
