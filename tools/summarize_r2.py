@@ -39,7 +39,9 @@ def capture(name):
     # units of work in the captured launch: executions of the kernel's 64-bit counter atomic
     its = [int(x["Instructions Executed"]) for x in csv.DictReader(io.StringIO("\n".join(src[s2:]))) if "RED" in x["Source"] and ".64" in x["Source"]]
     return dict(kernel=vals[hdr.index("Kernel Name")], dram_bytes=g("dram__bytes_read.sum") + g("dram__bytes_write.sum"),
-                duration_us=float(vals[hdr.index("gpu__time_duration.sum")].replace(",", "")), units=max(its) if its else None,
+                duration_us=float(vals[hdr.index("gpu__time_duration.sum")].replace(",", "")) *
+                {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(units[hdr.index("gpu__time_duration.sum")], 1.0),
+                units=max(its) if its else None,
                 registers=int(float(vals[hdr.index("launch__registers_per_thread")])),
                 issue_active_pct=float(vals[hdr.index("smsp__issue_active.avg.pct_of_peak_sustained_active")]),
                 warps_active_pct=float(vals[hdr.index("sm__warps_active.avg.pct_of_peak_sustained_active")]))
