@@ -63,6 +63,9 @@ struct SolverDev {
     int *counts;
     unsigned long long *counters;      // [0] RK4 steps, [1] Broyden iterations, [2] Jacobian factorisations, [3] dopri steps,
                                        // [4] residual requests, [5] Q passes, [16+k] / [32+k] phase clocks
+    const SolverDev *self;             // this struct in GLOBAL memory: what non-inlined device functions take by reference
+                                       // (a reference to the kernel parameter would make every thread copy the 2.5 KB
+                                       // struct to its local-memory frame)
     int jac_fast;                      // Jacobian phase: 1 = qrfac_w / qform_w (four lanes per column; A/B only)
     int jac_window;                    // Jacobian phase: 1 = register-window routines when the matrix has the block structure
     int sm_count;                      // multiprocessors of the device (seq_warp)
@@ -323,9 +326,14 @@ __device__ __noinline__ void assemble(const SolverDev &D, long b, int col, doubl
         }
         return jends_b + (size_t)(D.col_item0[col] + s) * D.REC;
     };
-    double tl[SOCP_MAX_NODES + 1], sw[2] = {0.0227, 0.08};
+    // node times on demand (timeline_pair per evaluated segment: no per-thread array of M + 1 times in local memory);
+    // the first call also yields the switching times the model context needs
+    double sw[2] = {0.0227, 0.08};
     const int nm = N * D.M;
-    timeline_all(D, D.time + b * (D.M + 1), [&](int k) { return xv(nm + k); }, tl, sw);
+    const double *time_b = D.time + b * (D.M + 1);
+    auto xfree = [&](int k) { return xv(nm + k); };
+    double t_lo, t_hi;
+    timeline_pair(D, time_b, xfree, seg_lo, t_lo, t_hi, sw);
     typename M::Ctx c;
     M::load(c, mp, sw);
     int nbr = nm;
@@ -337,7 +345,9 @@ __device__ __noinline__ void assemble(const SolverDev &D, long b, int col, doubl
             if (i == D.M - 1 && D.mode_t[D.M] != SOCP_FIXED) nbr += 1;
             continue;
         }
-        const double t2 = tl[i + 1];
+        double t1, t2, sw_unused[2];
+        if (i == seg_lo) { t1 = t_lo; t2 = t_hi; }
+        else timeline_pair(D, time_b, xfree, i, t1, t2, sw_unused);
         const double *e = rec(i);
 #pragma unroll
         for (int k = 0; k < N; ++k) { Xtf[k] = e[k]; X1[k] = xv(N * i + k); }
@@ -348,7 +358,7 @@ __device__ __noinline__ void assemble(const SolverDev &D, long b, int col, doubl
             for (int k = 0; k < n; ++k)
                 emit(k, (D.mode_X[0][k] == SOCP_FREE) ? X1[k + n] : X1[k] - Xb[k]);
             if (D.mode_t[0] != SOCP_FIXED) {
-                emit(nm, M::hamiltonian(c, tl[0], X1));
+                emit(nm, M::hamiltonian(c, t1, X1));
                 nbr += 1;
             }
         }
@@ -430,8 +440,11 @@ __global__ void __launch_bounds__(256) zero_fjac_kernel(SolverDev D, int cur) {
 // ---- kernel 2a: assemble residuals and forward-difference Jacobian columns ----------------------
 // One thread per residual request, one thread per (Jacobian request, column).  This is the only
 // solver kernel besides integrate_worklist that contains model code.
+#ifndef SOCP_ASM_MINB
+#define SOCP_ASM_MINB 1            // resident CTAs per SM asked of assemble_kernel (register cap: 1 -> 255, 3 -> 168, 4 -> 128)
+#endif
 template <int MODEL>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, SOCP_ASM_MINB)
 assemble_kernel(SolverDev D, int cur) {
     const int nres = D.counts[cur * 2 + 0], njac = D.analytic ? 0 : D.counts[cur * 2 + 1];
     const int *res_list = D.lists + (size_t)(cur * 2 + 0) * D.B;
@@ -446,7 +459,7 @@ assemble_kernel(SolverDev D, int cur) {
             const int trial = 1 - is[I_BASE];
             const double *te = D.ends + ((b * 2 + trial) * D.M) * D.REC;
             double *out = (is[I_PHASE] == PH_F0) ? D.fvec + b * n : D.wa4 + b * n;
-            assemble<MODEL>(D, b, -1, 0.0, te, D.jends + (size_t)b * D.nJ * D.REC, out, 0, D.M - 1, nullptr);
+            assemble<MODEL>(*D.self, b, -1, 0.0, te, D.jends + (size_t)b * D.nJ * D.REC, out, 0, D.M - 1, nullptr);
         } else {
             const long w2 = w - nres;
             const long b = jac_list[w2 / n];
@@ -461,7 +474,7 @@ assemble_kernel(SolverDev D, int cur) {
             const int N2 = 2 * Model<MODEL>::DIM, node = j / N2;
             const bool state_col = j < N2 * D.M;
             // fdjac1: the column was zero-filled (zero_fjac_kernel); only the reachable rows are written
-            assemble<MODEL>(D, b, j, h, be, D.jends + (size_t)b * D.nJ * D.REC, colj,
+            assemble<MODEL>(*D.self, b, j, h, be, D.jends + (size_t)b * D.nJ * D.REC, colj,
                             state_col ? max(node - 1, 0) : 0, state_col ? node : D.M - 1, fvec);
         }
     }

@@ -96,6 +96,7 @@ size_t carve(HostPlan &pl, void *blob, long Bw) {
     D.istate = c.take<int>(Bw * I_COUNT);
     D.lists = c.take<int>(4 * (size_t)Bw);
     D.counts = c.take<int>(8);
+    D.self = c.take<SolverDev>(1);
     return c.off + 256;
 }
 
@@ -394,6 +395,9 @@ int run_solver(socp_ctx *ctx, const socp_shape *shape, long B, const double *d_m
         D.time = d_time + first * (D.M + 1);
         D.Xb = d_Xb + first * (D.M + 1) * D.dim;
         const long nthreads = Bw * D.P;
+        // the wave's descriptor in global memory, for the device functions that take it by reference (pageable source:
+        // the copy is staged before the call returns)
+        CUDA_TRY(ctx, cudaMemcpyAsync((void *)D.self, &D, sizeof(SolverDev), cudaMemcpyHostToDevice, ctx->stream));
         CUDA_TRY(ctx, cudaMemsetAsync(D.counts, 0, 8 * sizeof(int), ctx->stream));
         solver_init<<<(unsigned)((nthreads + 255) / 256), 256, 0, ctx->stream>>>(D, d_x_in, first, d_active);
         ctx->launches += 1;
