@@ -441,7 +441,7 @@ __global__ void __launch_bounds__(256) zero_fjac_kernel(SolverDev D, int cur) {
 // One thread per residual request, one thread per (Jacobian request, column).  This is the only
 // solver kernel besides integrate_worklist that contains model code.
 #ifndef SOCP_ASM_MINB
-#define SOCP_ASM_MINB 1            // resident CTAs per SM asked of assemble_kernel (register cap: 1 -> 255, 3 -> 168, 4 -> 128)
+#define SOCP_ASM_MINB 3            // resident CTAs per SM asked of assemble_kernel (register cap 168; measured per 1e5-problem step: 191 ms uncapped at 230 registers, 174 ms at 168, 171 ms at 128 with more spills)
 #endif
 template <int MODEL>
 __global__ void __launch_bounds__(128, SOCP_ASM_MINB)
@@ -1766,18 +1766,34 @@ hybrd_qpass_kernel(SolverDev D, int cur) {
     if (tid == 0) mbar_init(bar, 1);
     __syncthreads();
     unsigned parity = 0;
+    // the index chain of a problem (list entry -> phase, pending flag) is two dependent global loads in front of the
+    // bulk copy: the next problem's is fetched while the current one is being worked on
+    long b_next = -1;
+    int phase_next = PH_IDLE, pend_next = 0;
+    if ((long)blockIdx.x < nres) {
+        b_next = res_list[blockIdx.x];
+        phase_next = D.istate[b_next * I_COUNT + I_PHASE];
+        pend_next = D.istate[b_next * I_COUNT + I_PEND];
+    }
     for (long g = blockIdx.x; g < nres; g += gridDim.x) {
-        const long b = res_list[g];
+        const long b = b_next;
+        const int phase = phase_next, pend = pend_next;
         int *is = D.istate + b * I_COUNT;
-        if (is[I_PHASE] != PH_TRIAL) continue;          // first residual of a solve: nothing to do (uniform)
-        const int pend = is[I_PEND];
+        if (g + gridDim.x < nres) {
+            b_next = res_list[g + gridDim.x];
+            phase_next = D.istate[b_next * I_COUNT + I_PHASE];
+            pend_next = D.istate[b_next * I_COUNT + I_PEND];
+        }
+        if (phase != PH_TRIAL) continue;                // first residual of a solve: nothing to do (uniform)
         double *Qg = D.fjac + (size_t)b * D.QS;
         if (tid == 0) {
             mbar_expect_tx(bar, qbytes);
             bulk_g2s(Qs, Qg, qbytes, bar);
         }
-        for (int i = tid; i < n; i += NT) wv[i] = D.wa4[b * n + i];
-        if (pend) for (int i = tid; i < 4 * n; i += NT) cf[i] = D.scr[b * 4 * (size_t)n + i];
+        // F(x + p) and the coefficient vectors with cp.async: every element in flight at once, next to the bulk copy
+        gcopy_async<NT>(wv, D.wa4 + b * n, n);
+        if (pend) gcopy_async<NT>(cf, D.scr + b * 4 * (size_t)n, 4 * n);
+        gcopy_async_wait();
         __syncthreads();
         while (!mbar_try_wait(bar, parity)) {}
         parity ^= 1u;
