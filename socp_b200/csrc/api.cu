@@ -46,6 +46,8 @@ struct socp_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    cudaStream_t stream2 = nullptr;      // Jacobian phase of a solver round, forked from / joined to `stream` with the two events
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     std::string err;
     std::vector<DevBuf> pool;            // workspace slots
     unsigned long long *d_counters = nullptr;   // [0] rk4 steps
@@ -218,7 +220,10 @@ int socp_create(int device, socp_ctx **out) {
     // every allocation of the context is checked: a half-built context is destroyed, never returned
     if ((e = cudaMalloc(&ctx->d_counters, 64 * sizeof(unsigned long long))) != cudaSuccess ||
         (e = cudaMemset(ctx->d_counters, 0, 64 * sizeof(unsigned long long))) != cudaSuccess ||
-        (e = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) {
+        (e = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming)) != cudaSuccess) {
         g_create_error = std::string("socp_create: ") + cudaGetErrorString(e);
         const int code = (e == cudaErrorMemoryAllocation) ? SOCP_ERR_NOMEM : SOCP_ERR_CUDA;
         cudaGetLastError();
@@ -239,6 +244,9 @@ void socp_destroy(socp_ctx *ctx) {
     if (ctx->d_counters) cudaFree(ctx->d_counters);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    if (ctx->stream2) { cudaStreamSynchronize(ctx->stream2); cudaStreamDestroy(ctx->stream2); }
     for (auto e : ctx->prof_events) cudaEventDestroy(e);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;

@@ -358,7 +358,10 @@ SOCP_DEV void obstacle_eval(double muObs, double phiObs, const double *pos, doub
 
 template <> struct Model<VTOL_UAV> {
     static constexpr int DIM = 6, N = 12, NP = 13, NCTRL = 3, DEFAULT_STEPS = 100;
-    static constexpr int MINB = 4;      // 128 registers: +45% throughput (occupancy hides the tanh chains)
+#ifndef SOCP_VTOL_MINB
+#define SOCP_VTOL_MINB 4
+#endif
+    static constexpr int MINB = SOCP_VTOL_MINB;      // 4: 128 registers, +45% throughput over 1 (occupancy hides the exp chains)
     // coop_lanes / cq / cmask: the thread mapping of the obstacle sum (see obstacle_eval), set by the cooperative kernels
     struct Ctx { double umax, amax, alphaT, alphaV, invSigma, Vd, ca, phiObs, muObs; int coop_lanes, cq; unsigned cmask; };
     SOCP_DEV static void load(Ctx &c, const double *m, const double *) {
@@ -415,7 +418,10 @@ template <> struct Model<VTOL_UAV> {
 
 template <> struct Model<INTERCEPTOR> {
     static constexpr int DIM = 6, N = 12, NP = 17, NCTRL = 2, DEFAULT_STEPS = 50;
-    static constexpr int MINB = 4;      // 128 registers: +65% throughput (occupancy hides the sin/cos chains)
+#ifndef SOCP_ICPT_MINB
+#define SOCP_ICPT_MINB 4
+#endif
+    static constexpr int MINB = SOCP_ICPT_MINB;      // 4: 128 registers, +65% throughput over 1 (occupancy hides the sin/cos chains)
     struct Ctx {
         double c0, hr, d0, eta, mprop, mempty, q, ve, alphamax, umax, mugft, muT, muV, muC;
         int chart, stage;

@@ -194,7 +194,8 @@ SmemPlan smem_plan(const SolverDev &D) {
 // context (one context = one device), never process-wide, so a second context on another GPU of the same
 // process configures its own copy and two host threads never share the table.
 template <typename K>
-int launch_smem(socp_ctx *ctx, K kernel, int grid, int threads, size_t smem, const SolverDev &D, int cur, int doubles) {
+int launch_smem(socp_ctx *ctx, K kernel, int grid, int threads, size_t smem, const SolverDev &D, int cur, int doubles,
+                cudaStream_t st = nullptr) {
     if (smem > 48 * 1024) {
         size_t &have = ctx->smem_configured[(const void *)kernel];
         if (smem > have) {
@@ -207,7 +208,7 @@ int launch_smem(socp_ctx *ctx, K kernel, int grid, int threads, size_t smem, con
             have = smem;
         }
     }
-    kernel<<<grid, threads, smem, ctx->stream>>>(D, cur, doubles);
+    kernel<<<grid, threads, smem, st ? st : ctx->stream>>>(D, cur, doubles);
     return SOCP_OK;
 }
 
@@ -242,6 +243,25 @@ void launch_hybrd(socp_ctx *ctx, const SolverDev &D, int cur, int grid, int prof
         else launch_smem(ctx, hybrd_jac_kernel<32, false, false>, g, thr, sp.bytes_jac, D, cur, sp.doubles_jac);
     } else {
         const bool full = g == D.sm_count * 6;
+        // The Broyden phase and the Jacobian phase of a round work on disjoint problems: outside profiled passes the
+        // Jacobian kernel runs on a second stream, forked after the assembly and joined before the next round, so that
+        // the partial waves of the two latency-bound kernels fill each other's idle SMs.  (SOCP_OVERLAP=0: one stream.)
+        static const bool overlap_on = !(getenv("SOCP_OVERLAP") && !strcmp(getenv("SOCP_OVERLAP"), "0"));
+        const bool overlap = overlap_on && prof_slot < 0 && ctx->stream2 != nullptr;
+        cudaStream_t sj = overlap ? ctx->stream2 : ctx->stream;
+        auto launch_jac = [&]() {
+            if (sp.stage_q_jac && sp.jac_r_global)          // R straight to global memory: one more CTA per SM
+                launch_smem(ctx, hybrd_jac_kernel<128, false, true>, g, thr, (size_t)(sp.doubles_jac - D.LR) * 8, D, cur, sp.doubles_jac - D.LR, sj);
+            else if (sp.stage_q_jac) launch_smem(ctx, hybrd_jac_kernel<128, true, true>, g, thr, sp.bytes_jac, D, cur, sp.doubles_jac, sj);
+            else if (sp.stage_r) launch_smem(ctx, hybrd_jac_kernel<128, true, false>, g, thr, sp.bytes_jac, D, cur, sp.doubles_jac, sj);
+            else launch_smem(ctx, hybrd_jac_kernel<128, false, false>, g, thr, sp.bytes_jac, D, cur, sp.doubles_jac, sj);
+        };
+        if (overlap) {
+            cudaEventRecord(ctx->ev_fork, ctx->stream);
+            cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0);
+            launch_jac();
+            cudaEventRecord(ctx->ev_join, ctx->stream2);
+        }
         if (sp.split) {
             // Q pass: one CTA per problem, a whole number of waves of resident CTAs when the round is full
             const int gq = full ? D.sm_count * sp.qpass_per_sm * 2 : g;
@@ -268,11 +288,8 @@ void launch_hybrd(socp_ctx *ctx, const SolverDev &D, int cur, int grid, int prof
         else launch_smem(ctx, hybrd_res_kernel<128, false>, g_res, thr, sp.bytes_res, D, cur, sp.doubles_res);
         }
         if (prof_slot >= 0) cudaEventRecord(prof_event(ctx, kProfEv * prof_slot + 4), ctx->stream);
-        if (sp.stage_q_jac && sp.jac_r_global)          // R straight to global memory: one more CTA per SM
-            launch_smem(ctx, hybrd_jac_kernel<128, false, true>, g, thr, (size_t)(sp.doubles_jac - D.LR) * 8, D, cur, sp.doubles_jac - D.LR);
-        else if (sp.stage_q_jac) launch_smem(ctx, hybrd_jac_kernel<128, true, true>, g, thr, sp.bytes_jac, D, cur, sp.doubles_jac);
-        else if (sp.stage_r) launch_smem(ctx, hybrd_jac_kernel<128, true, false>, g, thr, sp.bytes_jac, D, cur, sp.doubles_jac);
-        else launch_smem(ctx, hybrd_jac_kernel<128, false, false>, g, thr, sp.bytes_jac, D, cur, sp.doubles_jac);
+        if (overlap) cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0);
+        else launch_jac();
     }
 }
 

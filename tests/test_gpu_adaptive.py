@@ -44,6 +44,7 @@ def test_adaptive_matches_oracle(oracle_lib, model, tol):
     Xb = X0[None, :] * (1 + 1e-3 * rng.uniform(-1, 1, size=(5, X0.size)))
     Xb[0] = X0
     got, ns = engine().traj_adaptive_batch(model, mp, t0, Xb, tf, tol, steps)
+    on_path = 0
     for k in range(5):
         want, acc, rej = oracle_adaptive(model, mp, t0, Xb[k], tf, steps, tol)
         scale = np.max(np.abs(want))
@@ -53,7 +54,11 @@ def test_adaptive_matches_oracle(oracle_lib, model, tol):
         err = np.max(np.abs(got[k] - want)) / scale
         # on the same path the end points agree to rounding; the step sizes are continuous functions of
         # the error norm, so rounding differences move the time grid slightly over long integrations
-        assert err <= (1e-11 + 1e-3 * tol if same_path else 50 * tol), (model, tol, k, err, tuple(ns[k]), (acc, rej))
+        # off the path both runs still control the local error to tol: the end points differ by a few tol
+        assert err <= (1e-11 + 1e-3 * tol if same_path else 10 * tol), (model, tol, k, err, tuple(ns[k]), (acc, rej))
+        on_path += same_path
+    # a flipped controller decision is the exception: at least four of the five trajectories follow the checker's path
+    assert on_path >= 4, (model, tol, on_path)
     assert np.all(ns[:, 0] >= 1)
 
 
@@ -90,7 +95,7 @@ def test_solve_with_adaptive_segments(oracle_lib):
     o = p.solve(spec["x0"], xtol=spec["xtol"])
     assert int(r["info"][0]) == o["info"] == 1
     assert np.linalg.norm(r["x"][0] - o["x"]) <= 10 * spec["xtol"] * np.linalg.norm(o["x"])
-    assert abs(int(r["nfev"][0]) - o["nfev"]) <= 0.25 * o["nfev"]
+    assert abs(int(r["nfev"][0]) - o["nfev"]) <= 2, (int(r["nfev"][0]), o["nfev"])
     # and the RK4 solution is the same optimum (30 RK4 steps of a piecewise-polynomial flow are exact)
     ref = OracleBackend().solve(spec)
     assert np.linalg.norm(r["x"][0] - ref["x"]) <= 1e-6 * np.linalg.norm(ref["x"])
