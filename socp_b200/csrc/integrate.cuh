@@ -255,39 +255,29 @@ traj_kernel(long B, int S, const double *__restrict__ mparams, const double *__r
             double ode_tol, int *__restrict__ nsteps) {
     typedef Model<MODEL> M;
     constexpr int N = M::N;
-    // The states of a block's trajectories are contiguous in X0 / Xf ([B][N]): they cross global memory as ONE
-    // coalesced stream through a shared staging tile (row stride N + 1: odd, so the per-thread reads of a row are
-    // conflict-free) instead of N strided 8-byte accesses per thread (74 % excess sectors in the round-1 capture).
-    __shared__ double stage[(SOCP_TRAJ_THREADS / L) * (N + 1)];
+    // (State I/O is per thread, N strided 8-byte accesses: staging the block's states through a shared tile for coalesced
+    // traffic was measured -- 0.662 vs 0.582 ms for 2^20 Goddard trajectories, 51 vs 58 % of the FP64 peak: the two block
+    // barriers and the tile cost more than the 74 % excess sectors of a kernel that moves 300 B per 11 kflop.)
     const long gt = (long)blockIdx.x * blockDim.x + threadIdx.x;
     const long b = gt / L;
-    const int q = (int)(threadIdx.x % L), row = (int)(threadIdx.x / L);
-    const long b0 = ((long)blockIdx.x * blockDim.x) / L;
-    const long nb = max(0L, min((long)(blockDim.x / L), B - b0));
-    for (long e = threadIdx.x; e < nb * N; e += blockDim.x) stage[(e / N) * (N + 1) + (e % N)] = X0[b0 * N + e];
-    __syncthreads();
+    const int q = (int)(threadIdx.x % L);
     int steps = 0;
-    double X[N];
     if (b < B) {
         typename M::Ctx c;
         M::load(c, mparams + b * M::NP, sw ? sw + 2 * b : nullptr);
         if (L > 1) Coop<MODEL>::set(c, q, ((1u << L) - 1u) << ((threadIdx.x & 31) & ~(L - 1)));
+        double X[N];
 #pragma unroll
-        for (int i = 0; i < N; ++i) X[i] = stage[row * (N + 1) + i];
+        for (int i = 0; i < N; ++i) X[i] = X0[b * N + i];
         int rej = 0;
         if (ADAPTIVE) steps = compute_traj_adaptive<MODEL>(c, X, t0[b], tf[b], S, ode_tol, rej);
         else steps = compute_traj<MODEL>(c, X, t0[b], tf[b], S);
         if (q == 0) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) Xf[b * N + i] = X[i];
             if (nsteps) { nsteps[2 * b] = steps; nsteps[2 * b + 1] = rej; }
         } else steps = 0;
     }
-    __syncthreads();                                   // every thread has read its row of the tile
-    if (b < B && q == 0) {
-#pragma unroll
-        for (int i = 0; i < N; ++i) stage[row * (N + 1) + i] = X[i];
-    }
-    __syncthreads();
-    for (long e = threadIdx.x; e < nb * N; e += blockDim.x) Xf[b0 * N + e] = stage[(e / N) * (N + 1) + (e % N)];
     count_steps(counter + (ADAPTIVE ? 3 : 0), steps);
 }
 
