@@ -898,8 +898,13 @@ def main():
         dist.destroy_process_group()
 
 
+_PER_PROBLEM_CONT = ("time_des", "Xb_des", "goal")          # continuation data with one row per problem
+
+
 def _slice(w, lo, hi):
     w.mp, w.time, w.Xb, w.x0 = (np.ascontiguousarray(a[lo:hi]) for a in (w.mp, w.time, w.Xb, w.x0))
+    if w.cont:
+        w.cont = {k: (np.ascontiguousarray(v[lo:hi]) if k in _PER_PROBLEM_CONT else v) for k, v in w.cont.items()}
     return w
 
 
@@ -917,6 +922,9 @@ def _strong_block(build, eng, total, lo, hi, seed):
     w = parts[0]
     if len(parts) > 1:
         w.mp, w.time, w.Xb, w.x0 = (np.ascontiguousarray(np.concatenate([getattr(p, k) for p in parts])) for k in ("mp", "time", "Xb", "x0"))
+        if w.cont:
+            w.cont = {k: (np.ascontiguousarray(np.concatenate([p.cont[k] for p in parts])) if k in _PER_PROBLEM_CONT else v)
+                      for k, v in w.cont.items()}
     return w
 
 

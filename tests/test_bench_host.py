@@ -57,3 +57,27 @@ def test_reference_xstar_is_the_golden_solution():
     import bench
     x = bench.reference_xstar()
     assert x.shape == (85,) and abs(x[84] - 0.21965083876703931) < 1e-15      # tf of Goddard stage 1
+
+
+def test_strong_scaling_blocks_carry_every_per_problem_array():
+    """bench.py --scaling strong: a rank's block of the global batch is cut out of 100000-problem blocks drawn with
+    fixed seeds; every per-problem array -- the continuation targets too -- must follow the cut, whatever the
+    world size (a rank whose block spans two seed blocks included)."""
+    import bench
+    total = 250000
+    for build in (bench.wl_interceptor, bench.wl_covid19):
+        full = bench._strong_block(build, None, total, 0, total, 7)
+        assert full.B == total
+        for world in (2, 8):
+            per = -(-total // world)
+            for rank in (0, world - 1, world // 2):
+                lo, hi = min(rank * per, total), min(rank * per + per, total)
+                w = bench._strong_block(build, None, total, lo, hi, 7)
+                assert w.B == hi - lo
+                assert np.array_equal(w.x0, full.x0[lo:hi]) and np.array_equal(w.Xb, full.Xb[lo:hi])
+                for k in bench._PER_PROBLEM_CONT:
+                    if k in w.cont:
+                        assert w.cont[k].shape[0] == hi - lo, (k, w.cont[k].shape)
+                        assert np.array_equal(w.cont[k], full.cont[k][lo:hi]), k
+                s0 = w.spec(0)
+                assert s0["cont"]["step"] == w.cont["step"]
