@@ -81,3 +81,18 @@ def test_strong_scaling_blocks_carry_every_per_problem_array():
                         assert np.array_equal(w.cont[k], full.cont[k][lo:hi]), k
                 s0 = w.spec(0)
                 assert s0["cont"]["step"] == w.cont["step"]
+
+
+def test_ncu_traffic_record_belongs_to_these_sources():
+    """roofline.traffic is taken from profiles/r2_traffic.json only when that record was captured from the CUDA sources
+    being run (digest of socp_b200/csrc): the committed record must match the committed sources, and it must carry a
+    measured figure for the kernels of the Broyden and Jacobian phases."""
+    import json
+    import bench
+    with open(bench.TRAFFIC_FILE) as f:
+        t = json.load(f)
+    assert t["source_digest"] == bench.source_digest(), "re-run tools/profile_r2.sh + tools/summarize_r2.py after changing csrc/"
+    kernels, src = bench.ncu_traffic()
+    for name in ("hybrd_chain_kernel", "hybrd_qpass_kernel", "hybrd_jac_kernel"):
+        assert kernels[name]["dram_bytes_per_unit"] > 1e4 and kernels[name]["units"] > 100, name
+    assert "r2_traffic.json" in src
