@@ -406,10 +406,11 @@ def source_digest():
     return h.hexdigest()[:16]
 
 
-def ncu_traffic():
-    """DRAM bytes per unit of work of each solver kernel, extracted by tools/summarize_profiles.py from the
-    committed `ncu --set full` captures (profiles/r2_*_raw.csv).  Only used when it was captured from the
-    sources being run (digest match); otherwise traffic is reported as null."""
+def ncu_traffic(workload="goddard", P=85):
+    """DRAM bytes per unit of work of each solver kernel, extracted by tools/summarize_r2.py from the committed
+    `ncu --set full` captures (profiles/r2_*_raw.csv).  Only used when it was captured from the sources being run
+    (digest match) on the workload being run (the bytes per Broyden iteration or per factorisation scale with P^2);
+    otherwise traffic is reported as null."""
     try:
         with open(TRAFFIC_FILE) as f:
             t = json.load(f)
@@ -417,6 +418,8 @@ def ncu_traffic():
         return {}, "no ncu capture on record (profiles/r2_traffic.json absent)"
     if t.get("source_digest") != source_digest():
         return {}, "ncu capture on record is from other sources (digest %s, running %s)" % (t.get("source_digest"), source_digest())
+    if t.get("P", 85) != P or not workload.startswith(t.get("workload", "goddard")):
+        return {}, "ncu capture on record is of the %s workload (P = %d), not of this one" % (t.get("workload", "goddard"), t.get("P", 85))
     return t.get("kernels", {}), "profiles/r2_traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum)"
 
 
@@ -759,7 +762,7 @@ def main():
     flops = FLOPS_PER_RK4_STEP[w.flops_key]
     peak_tf = peak_gflops / 1e3
     hbm_peak, hbm_src = hbm_peak_gbs()
-    traffic, traffic_src = ncu_traffic()
+    traffic, traffic_src = ncu_traffic(w.name, P)
     roofline, whole = None, None
     if not args.no_profile_pass:
         eng.reset_stats()

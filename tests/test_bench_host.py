@@ -96,3 +96,7 @@ def test_ncu_traffic_record_belongs_to_these_sources():
     for name in ("hybrd_chain_kernel", "hybrd_qpass_kernel", "hybrd_jac_kernel"):
         assert kernels[name]["dram_bytes_per_unit"] > 1e4 and kernels[name]["units"] > 100, name
     assert "r2_traffic.json" in src
+    # the record is of the Goddard batch (P = 85): it is not applied to the kernels of another workload
+    assert bench.ncu_traffic("goddard_warm", 85)[0] == kernels
+    other, why = bench.ncu_traffic("covid19", 160)
+    assert other == {} and "not of this one" in why

@@ -47,7 +47,7 @@ def capture(name):
                 warps_active_pct=float(vals[hdr.index("sm__warps_active.avg.pct_of_peak_sustained_active")]))
 
 
-traffic = {"source_digest": bench.source_digest(), "tag": tag, "kernels": {}}
+traffic = {"source_digest": bench.source_digest(), "tag": tag, "workload": "goddard", "P": 85, "kernels": {}}      # profile_r2.sh captures the default workload
 names = {"chain": "hybrd_chain_kernel", "qpass": "hybrd_qpass_kernel", "jac": "hybrd_jac_kernel"}
 for short, full in names.items():
     try:
